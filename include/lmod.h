@@ -1,0 +1,180 @@
+/* lmod.h -- C ABI of liblmod_b200.so: the B200 (sm_100a) kernels behind the LLaVA-MoD
+ * distillation step.
+ *
+ * The reference (shufangxun/LLaVA-MoD) has NO plugin / FFI interface -- it is pure Python on
+ * PyTorch.  The boundary this library replaces is therefore the set of
+ * PyTorch call sites on the hot path; every entry point cites the reference lines whose GPU
+ * work it takes over.  Conventions (all entry points):
+ *   - plain pointers and sizes, no torch types; device pointers are BORROWED for the call;
+ *   - no allocation, no host sync, no stream creation inside; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*);  re-entrant across streams;
+ *   - return 0 on success, negative lmod_status on error; lmod_last_error() gives a
+ *     thread-local message;
+ *   - bf16 tensors are row-major; `ld*` are row strides in ELEMENTS.
+ */
+#ifndef LMOD_H_
+#define LMOD_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  LMOD_OK = 0,
+  LMOD_ERR_ARG = -1,      /* bad argument (shape / alignment / null)         */
+  LMOD_ERR_CUDA = -2,     /* CUDA runtime error (see lmod_last_error)        */
+  LMOD_ERR_UNSUPPORTED = -3
+} lmod_status;
+
+const char* lmod_last_error(void);
+int lmod_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+int64_t lmod_launch_count(void);
+void lmod_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K16 + K15: fused mimic-KL (+ shifted LM cross-entropy) forward AND backward over the vocab.
+ * Replaces AlignTrainer.get_p / get_logp / compute_align_loss (llavamod/train/align_trainer.py:
+ * 473-475, 497-499, 509-526) and the model's shifted CE (llava_qwen1_5_moe.py:413-421).
+ *   s_logits [N, ld_s] bf16 student, t_logits [N, ld_t] bf16 teacher, labels [N] int64
+ *   (post-splice, row n = b*T + t).  V = vocab slice (151936).  Per row n:
+ *     x_n   = sum_v p_T(v) * log q_S(v)           (0 where log q_S is +-inf)
+ *     nll_n = lse_S - s[labels[n+1]]              (t < T-1 and label != -100)
+ *   dlogits[n,v] = w_kd*m_n/n_kd*(q_S - p_T) + w_ce*c_n/n_ce*(q_S - onehot)  (bf16; may alias s_logits)
+ *   with m_n = labels[n] != -100 (or 1 if distill_all), c_n = CE mask, counts from lmod_kl_counts.
+ *   row_out [N,4] fp32 = {x_n, nll_n, lse_S, lse_T};  dlogits may be NULL (forward only).
+ */
+int lmod_kl_counts(const int64_t* labels, int64_t n_rows, int64_t seq_len, int distill_all,
+                   float* counts2 /* {n_kd, n_ce} */, void* stream);
+int lmod_kl_fwd_bwd(const void* s_logits, int64_t ld_s, const void* t_logits, int64_t ld_t,
+                    const int64_t* labels, int64_t n_rows, int64_t seq_len, int64_t vocab,
+                    int distill_all, float w_kd, float w_ce, const float* counts2,
+                    float* row_out, void* dlogits, int64_t ld_d, void* stream);
+/* reduces row_out into {align_loss, ce_loss, n_kd, n_ce} (align = -sum m x / n_kd ; 0/0 -> NaN kept,
+ * align_trainer.py:526) */
+int lmod_kl_finalize(const float* row_out, const int64_t* labels, int64_t n_rows, int64_t seq_len,
+                     int distill_all, float* out4, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K17: DPO per-token log-prob gather.  Replaces DPOTrainer.get_logp (dpo_trainer.py:483-495):
+ * labels shifted by one, NO vocab slice, log_softmax + gather + masked sequence sum.
+ *   fwd: tok_logp [N] fp32 (0 for masked rows), lse [N] fp32, seq_logp [B] fp32
+ *   bwd: dlogits[n,v] = g_seq[b]*mask_n*(onehot - q)   (bf16; may alias logits)
+ */
+int lmod_logp_gather_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t batch,
+                         int64_t seq_len, int64_t vocab, float* tok_logp, float* lse,
+                         float* seq_logp, int average, void* stream);
+int lmod_logp_gather_bwd(const void* logits, int64_t ld, const int64_t* labels, int64_t batch,
+                         int64_t seq_len, int64_t vocab, const float* lse, const float* g_seq,
+                         int average, void* dlogits, int64_t ld_d, void* stream);
+
+/* API-compat materialising forms of get_p / get_logp (fp32 [N,V] outputs) and compute_align_loss
+ * on materialised inputs (align_trainer.py:473-528). */
+int lmod_softmax_rows(const void* logits_bf16, int64_t ld, int64_t n_rows, int64_t vocab,
+                      int log_mode, float* out, int64_t ld_out, void* stream);
+int lmod_align_loss_dense(const float* logp, const float* probs, int64_t ld, const int64_t* labels,
+                          int64_t n_rows, int64_t vocab, int distill_all, float* row_x,
+                          float* out_loss, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K10 + K11: DeepSpeed-0.9.5 top-2 gate + capacity + token scatter in ONE cooperative kernel.
+ * Replaces deepspeed.moe.sharded_moe.TopKGate/top2gating + the dispatch einsum
+ * (call site llava_qwen1_5_moe.py:536-546).
+ *   x [S,H] bf16, wg [E,H] fp32, noise [S,E] fp32 (Gumbel, explicit input).
+ *   outputs: logits [S,E] fp32, gates [S,E] fp32, idx [S,2] int32, row [S,2] int32 (-1 = dropped),
+ *            w [S,2] fp32 (normalised, 0 if dropped), offsets [E+1] int32 (row ranges per expert),
+ *            meta [4+E] fp32 {l_aux, capacity, rows_total, 0, exp_counts...}, xp [2S,H] bf16 permuted.
+ *   sync_ws: >= 16 bytes of zero-initialised device scratch (grid barrier), reset by the kernel.
+ */
+/* capacity_factor < 0 selects capacity-padded slabs (offsets[e] = e*C, |cf| used) instead of compact rows. */
+int lmod_moe_capacity(int64_t S, int E, float capacity_factor, int64_t min_capacity);
+int lmod_moe_route_scatter(const void* x, const float* wg, const float* noise, int64_t S, int64_t H,
+                           int E, float capacity_factor, int64_t min_capacity,
+                           float* logits, float* gates, int32_t* idx, int32_t* row, float* w,
+                           int32_t* offsets, float* meta, void* xp, int32_t* sync_ws, void* stream);
+/* combine einsum("sec,ecm->sm") with bf16-rounded weights + optional residual add (Appendix A step 11,
+ * llava_qwen1_5_moe.py:167) */
+int lmod_moe_gather_combine(const void* y, const int32_t* row, const float* w, const void* residual,
+                            int64_t S, int64_t H, void* out, void* stream);
+/* backward of gather_combine: dY rows + d(w) per choice */
+int lmod_moe_combine_bwd(const void* dout, const void* y, const int32_t* row, const float* w,
+                         int64_t S, int64_t H, void* dy, float* dw, void* stream);
+/* backward of the gate: (dw, l_aux upstream grad) -> dlogits [S,E] fp32 */
+int lmod_moe_gate_bwd(const float* gates, const int32_t* idx, const int32_t* row, const float* dw,
+                      const float* meta, const float* g_laux, int64_t S, int E, float* dlogits,
+                      void* stream);
+/* dx[s] = dxp[row1] + dxp[row2] + sum_e dlogits[s,e]*wg[e] (+ dres) ; and dwg partial sums */
+int lmod_moe_scatter_bwd(const void* dxp, const int32_t* row, const float* dlogits, const float* wg,
+                         const void* dres, int64_t S, int64_t H, int E, void* dx, void* stream);
+int lmod_moe_wg_grad(const void* x, const float* dlogits, int64_t S, int64_t H, int E,
+                     float* ws /* [32,E,H] */, float* dwg /* [E,H], accumulated (+=) */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4/K6/K9/K2/K1 element-wise + norm kernels (modeling_qwen2.py:105-110,159-184,199-200;
+ * multimodal_projector/builder.py:57-61; transformers CLIP LayerNorm/quick_gelu).
+ */
+int lmod_rmsnorm_fwd(const void* x, const void* res /* optional: x := x + res first */, const void* w,
+                     int64_t rows, int64_t H, float eps, void* y, void* x_out /* x+res, optional */,
+                     float* rstd, void* stream);
+int lmod_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
+                     int64_t rows, int64_t H, void* dx, void* stream);
+int lmod_layernorm_fwd(const void* x, const void* w, const void* b, int64_t rows, int64_t H, float eps,
+                       void* y, void* stream);
+/* rotate-half RoPE applied in place to q [rows, nh*hd] and k [rows, nkv*hd] (rows of a fused QKV buffer via ld).
+ * cos/sin tables are the reference's bf16 cache ([max_pos, hd], modeling_qwen2.py:127-136) gathered by position_ids. */
+int lmod_rope(void* q, int64_t ld_q, int nh, void* k, int64_t ld_k, int nkv, int hd,
+              const void* cos_table, const void* sin_table, const int64_t* position_ids, int64_t rows,
+              int backward, void* stream);
+int lmod_silu_mul_fwd(const void* gate_up, int64_t ld, int64_t rows, int64_t I, void* out, void* stream);
+int lmod_silu_mul_bwd(const void* dout, const void* gate_up, int64_t ld, int64_t rows, int64_t I,
+                      void* dgate_up, void* stream);
+/* act: 0 = gelu(erf), 1 = quick_gelu ; in place allowed; optional bias [n] added first */
+int lmod_bias_act_fwd(const void* x, const void* bias, int64_t rows, int64_t n, int act, void* y,
+                      void* stream);
+int lmod_gelu_bwd(const void* dy, const void* x_pre, int64_t count, void* dx, void* stream);
+int lmod_add(const void* a, const void* b, int64_t count, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3: multimodal splice (llava_arch.py:228-320): src [B*T'] int64 plan (>=0 token id, -1-k image
+ * row k, other = padding), img_index [B*T'] int64.
+ */
+int lmod_splice_embed(const void* embed_w, const void* feats, const int64_t* src, const int64_t* img_index,
+                      int64_t n_rows, int64_t H, int64_t n_patches, void* out, void* stream);
+int lmod_splice_embed_bwd(const void* dout, const int64_t* src, const int64_t* img_index, int64_t n_rows,
+                          int64_t H, int64_t n_patches, void* dfeats /* pre-zeroed */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K19: fused AdamW on flat buffers (fp32 master/moments, bf16 model copy), global-norm clip.
+ * Replaces DeepSpeed ZeRO-2 + CPUAdam (align_trainer.py:404-417; zero2_offload.json).
+ */
+int lmod_sumsq(const void* g_bf16_or_f32, int is_f32, int64_t count, float* out_accum /* += */, void* stream);
+int lmod_adamw(float* master, float* m, float* v, const void* grad, int grad_is_f32, void* model_bf16,
+               int64_t count, float lr, float beta1, float beta2, float eps, float wd, int64_t step,
+               const float* gnorm_sq /* optional */, float max_norm, float grad_scale, void* stream);
+
+/*LMOD_PLANNED_BEGIN
+/ * ------------------------------------------------------------------------------------------
+ * K5/K8/K9/K12/K14: tcgen05 + TMA GEMM  D[M,N] = A[M,K] * B[N,K]^T (+epilogue), bf16 in, fp32 TMEM
+ * accumulate, bf16 out.  Replaces nn.Linear call sites (modeling_qwen2.py:199-200,678-680,726,1176).
+ *   trans flags select K-major ('T') vs MN-major ('N') operands so that dgrad / wgrad need no copies.
+ *   grouped form: per-expert row ranges from `offsets` (device), weights [E,N,K].
+ * /
+int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                   void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, const void* bias,
+                   const void* residual, int64_t ldr, int epilogue, float* d_f32_accum, void* stream);
+int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t b_expert_stride,
+                           void* D, int64_t ldd, const int32_t* offsets, int E, int64_t max_rows,
+                           int64_t N, int64_t K, int mode, void* stream);
+
+/ * K7 attention (modeling_qwen2.py:713-721): causal / non-causal flash attention forward, bf16. * /
+int lmod_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, int64_t batch,
+                  int64_t seq, int nh, int nkv, int hd, int causal, const int32_t* seqlens,
+                  void* out, int64_t ld_o, float* lse, void* stream);
+
+LMOD_PLANNED_END*/
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMOD_H_ */

@@ -1,0 +1,369 @@
+// kl.cu -- fused mimic-KL (+ shifted CE) forward+backward over the vocabulary.
+//
+// Replaces (reference) llavamod/train/align_trainer.py:473-475 (teacher softmax fp32), :497-499
+// (student log_softmax fp32), :509-526 (product / masked_fill / vocab sum / masked mean) and
+// llava_qwen1_5_moe.py:413-421 (shifted CE), i.e. >= 8 full [N,V] passes, by ONE sweep:
+//
+//   * a row (V = 151936 bf16 logits, student + teacher = 608 KB) does not fit one SM's shared
+//     memory, so a thread-block CLUSTER of 8 CTAs owns a row: each CTA pulls its 1/8 slice of both
+//     rows into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx),
+//     reduces max / sum-exp / sum p_T*s locally, exchanges 6 floats through distributed shared
+//     memory (one barrier.cluster per row), then produces the gradient slice from the SAME shared
+//     memory copy.  HBM traffic is therefore exactly the algorithmic 4*V bytes read + 2*V written
+//     per token; nothing is re-read.
+//   * two CTAs are resident per SM (<= 2 x 76 KB smem) so one CTA's loads overlap the other's math.
+//   * rows whose KD mask and CE mask are both 0 contribute nothing (reference multiplies by 0):
+//     their loads are skipped and their gradient slice is zero-filled.
+#include "common.cuh"
+
+namespace {
+
+constexpr int KL_THREADS = 256;
+constexpr int KL_CHUNKS = 4;       // mbarrier-tracked load chunks per slice
+constexpr int KL_MAX_CS = 8;
+
+struct KlParams {
+  const __nv_bfloat16* s;
+  const __nv_bfloat16* t;
+  const int64_t* labels;
+  const float* counts;   // {n_kd, n_ce}
+  float* row_out;        // [N,4]
+  __nv_bfloat16* d;      // may be null / alias s
+  int64_t ld_s, ld_t, ld_d;
+  int64_t n_rows, seq_len;
+  int vocab, slice;      // slice: elements per CTA (multiple of 8)
+  int distill_all;
+  float w_kd, w_ce;
+};
+
+struct Xchg {            // per-CTA partials published to the cluster
+  float ms, mt, zs, zt, a, slab, pad0, pad1;
+};
+
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t hmin2_u32(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmin2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <bool CHECK_INF>
+__device__ __forceinline__ void accum_pair(uint32_t sw, uint32_t tw, float nms, float nmt, float& zs,
+                                           float& zt, float& a) {
+  float s0 = bf16lo(sw), s1 = bf16hi(sw), t0 = bf16lo(tw), t1 = bf16hi(tw);
+  float es0 = ex2f(fmaf(s0, LOG2E_F, nms)), es1 = ex2f(fmaf(s1, LOG2E_F, nms));
+  float et0 = ex2f(fmaf(t0, LOG2E_F, nmt)), et1 = ex2f(fmaf(t1, LOG2E_F, nmt));
+  zs += es0; zs += es1;
+  zt += et0; zt += et1;
+  if (CHECK_INF) {   // align_trainer.py:509-510: terms where log q_S is +-inf are dropped
+    if (isinf(s0)) { s0 = 0.f; et0 = 0.f; }
+    if (isinf(s1)) { s1 = 0.f; et1 = 0.f; }
+  }
+  a = fmaf(et0, s0, a);
+  a = fmaf(et1, s1, a);
+}
+
+__global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(16) Xchg xchg[2];
+  __shared__ __align__(8) uint64_t bars[KL_CHUNKS];
+  __shared__ float red[6][KL_THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank(), cs = cluster_nctarank();
+  const uint32_t cid = cluster_id_x(), ncl = cluster_nclusters_x();
+
+  uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
+  uint4* t_buf = reinterpret_cast<uint4*>(smem_raw + (size_t)p.slice * 2);
+
+  // this CTA's slice of the vocabulary
+  const int v0 = (int)rank * p.slice;
+  int len = p.vocab - v0;
+  len = len < 0 ? 0 : (len > p.slice ? p.slice : len);
+  const int nvec = len >> 3;                                   // 16-byte vectors (8 bf16)
+  const int cvec = ((nvec + KL_CHUNKS - 1) / KL_CHUNKS);        // vectors per chunk
+
+  if (tid == 0) {
+    for (int c = 0; c < KL_CHUNKS; ++c) mbar_init(&bars[c], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  const float n_kd = p.counts[0], n_ce = p.counts[1];
+  uint32_t it_active = 0;
+
+  for (int64_t row = cid; row < p.n_rows; row += ncl) {
+    // ---- masks (uniform over the cluster) ----
+    const int64_t lab_here = p.labels[row];
+    const int64_t tpos = row % p.seq_len;
+    int64_t lab_next = LMOD_IGNORE_INDEX;
+    if (tpos + 1 < p.seq_len) lab_next = p.labels[row + 1];
+    const bool m_kd = p.distill_all ? true : (lab_here != LMOD_IGNORE_INDEX);
+    const bool m_ce = (lab_next != LMOD_IGNORE_INDEX);   // nll is always reported (loss/lm metric); w_ce only scales its gradient
+    const bool active = m_kd || m_ce;
+
+    if (!active) {
+      if (p.d != nullptr) {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* dst = reinterpret_cast<uint4*>(p.d + row * p.ld_d + v0);
+        for (int i = tid; i < nvec; i += KL_THREADS) stg_v4(dst + i, z);
+      }
+      if (rank == 0 && tid == 0) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(p.row_out + row * 4) = o;
+      }
+      continue;
+    }
+    const uint32_t par = it_active & 1u;
+    ++it_active;
+
+    // ---- issue the slice loads (1-D TMA bulk copies), chunked so math can start early ----
+    if (tid == 0 && nvec > 0) {
+      const __nv_bfloat16* srow = p.s + row * p.ld_s + v0;
+      const __nv_bfloat16* trow = p.t + row * p.ld_t + v0;
+      for (int c = 0; c < KL_CHUNKS; ++c) {
+        int b = c * cvec, e = min(nvec, b + cvec);
+        if (e <= b) { mbar_arrive(&bars[c]); continue; }
+        uint32_t bytes = (uint32_t)(e - b) * 16u;
+        mbar_expect_tx(&bars[c], 2 * bytes);
+        bulk_g2s(s_buf + b, srow + (size_t)b * 8, bytes, &bars[c]);
+        bulk_g2s(t_buf + b, trow + (size_t)b * 8, bytes, &bars[c]);
+      }
+    }
+
+    // ---- pass A: slice max (and min of s, to detect -inf logits) ----
+    uint32_t mxs = 0xff80ff80u, mxt = 0xff80ff80u, mns = 0x7f807f80u;   // bf16x2 (-inf,-inf) / (+inf,+inf)
+    if (nvec > 0) {
+      for (int c = 0; c < KL_CHUNKS; ++c) {
+        int b = c * cvec, e = min(nvec, b + cvec);
+        mbar_wait(&bars[c], par);
+        for (int i = b + tid; i < e; i += KL_THREADS) {
+          uint4 sv = s_buf[i], tv = t_buf[i];
+          uint32_t a = hmax2_u32(hmax2_u32(sv.x, sv.y), hmax2_u32(sv.z, sv.w));
+          uint32_t bb = hmax2_u32(hmax2_u32(tv.x, tv.y), hmax2_u32(tv.z, tv.w));
+          uint32_t cmin = hmin2_u32(hmin2_u32(sv.x, sv.y), hmin2_u32(sv.z, sv.w));
+          mxs = hmax2_u32(mxs, a);
+          mxt = hmax2_u32(mxt, bb);
+          mns = hmin2_u32(mns, cmin);
+        }
+      }
+    }
+    float ms = fmaxf(bf16lo(mxs), bf16hi(mxs));
+    float mt = fmaxf(bf16lo(mxt), bf16hi(mxt));
+    float mn = fminf(bf16lo(mns), bf16hi(mns));
+    ms = warp_max(ms); mt = warp_max(mt); mn = -warp_max(-mn);
+    if (lane == 0) { red[0][warp] = ms; red[1][warp] = mt; red[2][warp] = mn; }
+    __syncthreads();
+    {
+      float a = (lane < KL_THREADS / 32) ? red[0][lane] : -INFINITY;
+      float b = (lane < KL_THREADS / 32) ? red[1][lane] : -INFINITY;
+      float c = (lane < KL_THREADS / 32) ? red[2][lane] : INFINITY;
+      ms = warp_max(a); mt = warp_max(b); mn = -warp_max(-c);
+    }
+    const bool has_inf = isinf(mn) || isinf(ms);
+    const float ms_u = isinf(ms) ? 0.f : ms, mt_u = isinf(mt) ? 0.f : mt;   // guard (-inf) - (-inf)
+
+    // ---- pass B: local sum-exp and sum e^{t-mt} * s ----
+    float zs = 0.f, zt = 0.f, acc = 0.f;
+    {
+      const float nms = -ms_u * LOG2E_F, nmt = -mt_u * LOG2E_F;
+      if (!has_inf) {
+        for (int i = tid; i < nvec; i += KL_THREADS) {
+          uint4 sv = s_buf[i], tv = t_buf[i];
+          accum_pair<false>(sv.x, tv.x, nms, nmt, zs, zt, acc);
+          accum_pair<false>(sv.y, tv.y, nms, nmt, zs, zt, acc);
+          accum_pair<false>(sv.z, tv.z, nms, nmt, zs, zt, acc);
+          accum_pair<false>(sv.w, tv.w, nms, nmt, zs, zt, acc);
+        }
+      } else {
+        for (int i = tid; i < nvec; i += KL_THREADS) {
+          uint4 sv = s_buf[i], tv = t_buf[i];
+          accum_pair<true>(sv.x, tv.x, nms, nmt, zs, zt, acc);
+          accum_pair<true>(sv.y, tv.y, nms, nmt, zs, zt, acc);
+          accum_pair<true>(sv.z, tv.z, nms, nmt, zs, zt, acc);
+          accum_pair<true>(sv.w, tv.w, nms, nmt, zs, zt, acc);
+        }
+      }
+    }
+    zs = warp_sum(zs); zt = warp_sum(zt); acc = warp_sum(acc);
+    if (lane == 0) { red[3][warp] = zs; red[4][warp] = zt; red[5][warp] = acc; }
+    __syncthreads();
+    if (warp == 0) {
+      float a = (lane < KL_THREADS / 32) ? red[3][lane] : 0.f;
+      float b = (lane < KL_THREADS / 32) ? red[4][lane] : 0.f;
+      float c = (lane < KL_THREADS / 32) ? red[5][lane] : 0.f;
+      a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+      if (lane == 0) {
+        float slab = 0.f;
+        if (m_ce) {
+          int64_t off = lab_next - v0;
+          if (off >= 0 && off < len)
+            slab = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s_buf)[off]);
+        }
+        Xchg x;
+        x.ms = (nvec > 0) ? ms : -INFINITY; x.mt = (nvec > 0) ? mt : -INFINITY;
+        x.zs = a; x.zt = b; x.a = c; x.slab = slab; x.pad0 = 0.f; x.pad1 = 0.f;
+        xchg[par] = x;
+      }
+    }
+    // ---- cluster exchange through distributed shared memory ----
+    cluster_sync_all();
+    float lse_s, lse_t, xrow, slab;
+    {
+      float r_ms = -INFINITY, r_mt = -INFINITY, r_zs = 0.f, r_zt = 0.f, r_a = 0.f, r_sl = 0.f;
+      if ((uint32_t)lane < cs) {
+        const float* base = reinterpret_cast<const float*>(&xchg[par]);
+        r_ms = dsmem_ld_f32(base + 0, lane); r_mt = dsmem_ld_f32(base + 1, lane);
+        r_zs = dsmem_ld_f32(base + 2, lane); r_zt = dsmem_ld_f32(base + 3, lane);
+        r_a = dsmem_ld_f32(base + 4, lane);  r_sl = dsmem_ld_f32(base + 5, lane);
+      }
+      float Ms = warp_max(r_ms), Mt = warp_max(r_mt);
+      float Ms_u = isinf(Ms) ? 0.f : Ms, Mt_u = isinf(Mt) ? 0.f : Mt;
+      float fs = isinf(r_ms) ? 0.f : ex2f((r_ms - Ms_u) * LOG2E_F);
+      float ft = isinf(r_mt) ? 0.f : ex2f((r_mt - Mt_u) * LOG2E_F);
+      float Zs = warp_sum(r_zs * fs), Zt = warp_sum(r_zt * ft), A = warp_sum(r_a * ft);
+      slab = warp_sum(r_sl);
+      lse_s = Ms_u + lg2f(Zs) * LN2_F;
+      lse_t = Mt_u + lg2f(Zt) * LN2_F;
+      xrow = A / Zt - lse_s;
+    }
+    if (rank == 0 && tid == 0) {
+      float4 o = make_float4(xrow, m_ce ? (lse_s - slab) : 0.f, lse_s, lse_t);
+      *reinterpret_cast<float4*>(p.row_out + row * 4) = o;
+    }
+
+    // ---- pass C: gradient slice straight from shared memory ----
+    if (p.d != nullptr) {
+      const float ckd = m_kd ? (p.w_kd / n_kd) : 0.f;
+      const float cce = m_ce ? (p.w_ce / n_ce) : 0.f;
+      const float ca = ckd + cce, cb = ckd;
+      const float es = -lse_s * LOG2E_F, et = -lse_t * LOG2E_F;
+      const int lab_local = m_ce ? (int)(lab_next - v0) : -1;
+      uint4* dst = reinterpret_cast<uint4*>(p.d + row * p.ld_d + v0);
+      for (int i = tid; i < nvec; i += KL_THREADS) {
+        uint4 sv = s_buf[i], tv = t_buf[i];
+        float g[8];
+        const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+        const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float q0 = ex2f(fmaf(bf16lo(sw[j]), LOG2E_F, es)), q1 = ex2f(fmaf(bf16hi(sw[j]), LOG2E_F, es));
+          float p0 = ex2f(fmaf(bf16lo(tw[j]), LOG2E_F, et)), p1 = ex2f(fmaf(bf16hi(tw[j]), LOG2E_F, et));
+          g[2 * j] = fmaf(ca, q0, -cb * p0);
+          g[2 * j + 1] = fmaf(ca, q1, -cb * p1);
+        }
+        const unsigned rel = (unsigned)(lab_local - i * 8);
+        if (rel < 8u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (rel == (unsigned)j) g[j] -= cce;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+        o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+        stg_v4(dst + i, o);
+      }
+    }
+    __syncthreads();   // all generic-proxy reads of the slice are done before the next bulk load lands
+  }
+  cluster_sync_all();  // keep this CTA's shared memory alive until every peer finished its DSMEM reads
+}
+
+__global__ void kl_counts_kernel(const int64_t* __restrict__ labels, int64_t n, int64_t T, int distill_all,
+                                 float* __restrict__ out) {
+  __shared__ float red[32];
+  float a = 0.f, b = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    a += (distill_all || labels[i] != LMOD_IGNORE_INDEX) ? 1.f : 0.f;
+    if ((i % T) + 1 < T) b += (labels[i + 1] != LMOD_IGNORE_INDEX) ? 1.f : 0.f;
+  }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+__global__ void kl_finalize_kernel(const float* __restrict__ row_out, const int64_t* __restrict__ labels,
+                                   int64_t n, int64_t T, int distill_all, float* __restrict__ out) {
+  __shared__ float red[32];
+  float sx = 0.f, sn = 0.f, ck = 0.f, cc = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float4 r = *reinterpret_cast<const float4*>(row_out + i * 4);
+    bool m = distill_all || labels[i] != LMOD_IGNORE_INDEX;
+    bool c = ((i % T) + 1 < T) && labels[i + 1] != LMOD_IGNORE_INDEX;
+    if (m) { sx += r.x; ck += 1.f; }
+    if (c) { sn += r.y; cc += 1.f; }
+  }
+  sx = block_sum(sx, red); sn = block_sum(sn, red); ck = block_sum(ck, red); cc = block_sum(cc, red);
+  if (threadIdx.x == 0) {
+    out[0] = -sx / ck;     // 0/0 -> NaN like align_trainer.py:526
+    out[1] = sn / cc;
+    out[2] = ck;
+    out[3] = cc;
+  }
+}
+
+}  // namespace
+
+extern "C" int lmod_kl_counts(const int64_t* labels, int64_t n_rows, int64_t seq_len, int distill_all,
+                              float* counts2, void* stream) {
+  LMOD_CHECK_ARG(labels && counts2 && n_rows > 0 && seq_len > 0 && n_rows % seq_len == 0,
+                 "lmod_kl_counts: bad arguments (n_rows=%lld seq_len=%lld)", (long long)n_rows, (long long)seq_len);
+  kl_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(labels, n_rows, seq_len, distill_all, counts2);
+  LMOD_LAUNCH_OK();
+  return LMOD_OK;
+}
+
+extern "C" int lmod_kl_finalize(const float* row_out, const int64_t* labels, int64_t n_rows, int64_t seq_len,
+                                int distill_all, float* out4, void* stream) {
+  LMOD_CHECK_ARG(row_out && labels && out4 && n_rows > 0 && seq_len > 0, "lmod_kl_finalize: bad arguments");
+  kl_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_out, labels, n_rows, seq_len, distill_all, out4);
+  LMOD_LAUNCH_OK();
+  return LMOD_OK;
+}
+
+extern "C" int lmod_kl_fwd_bwd(const void* s_logits, int64_t ld_s, const void* t_logits, int64_t ld_t,
+                               const int64_t* labels, int64_t n_rows, int64_t seq_len, int64_t vocab,
+                               int distill_all, float w_kd, float w_ce, const float* counts2,
+                               float* row_out, void* dlogits, int64_t ld_d, void* stream) {
+  LMOD_CHECK_ARG(s_logits && t_logits && labels && counts2 && row_out, "lmod_kl_fwd_bwd: null pointer");
+  LMOD_CHECK_ARG(n_rows > 0 && seq_len > 0 && n_rows % seq_len == 0, "lmod_kl_fwd_bwd: n_rows %% seq_len != 0");
+  LMOD_CHECK_ARG(vocab >= 8 && vocab % 8 == 0 && ld_s % 8 == 0 && ld_t % 8 == 0 && ld_s >= vocab && ld_t >= vocab,
+                 "lmod_kl_fwd_bwd: vocab and row strides must be multiples of 8 elements (16-byte TMA bulk copies)");
+  LMOD_CHECK_ARG(((uintptr_t)s_logits % 16 == 0) && ((uintptr_t)t_logits % 16 == 0), "lmod_kl_fwd_bwd: pointers must be 16B aligned");
+  if (dlogits) LMOD_CHECK_ARG(ld_d % 8 == 0 && ld_d >= vocab && ((uintptr_t)dlogits % 16 == 0), "lmod_kl_fwd_bwd: bad dlogits stride");
+
+  int cs = (vocab >= 512) ? KL_MAX_CS : 1;
+  int64_t per = (vocab + cs - 1) / cs;
+  int slice = (int)((per + 7) / 8 * 8);
+  size_t smem = (size_t)slice * 2 * 2;
+  LMOD_CHECK_ARG(smem <= 220 * 1024, "lmod_kl_fwd_bwd: vocab %lld too large for the 8-CTA cluster layout", (long long)vocab);
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    LMOD_CUDA_OK(cudaFuncSetAttribute(kl_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_done = true;
+  }
+  KlParams p;
+  p.s = (const __nv_bfloat16*)s_logits; p.t = (const __nv_bfloat16*)t_logits; p.labels = labels;
+  p.counts = counts2; p.row_out = row_out; p.d = (__nv_bfloat16*)dlogits;
+  p.ld_s = ld_s; p.ld_t = ld_t; p.ld_d = ld_d; p.n_rows = n_rows; p.seq_len = seq_len;
+  p.vocab = (int)vocab; p.slice = slice; p.distill_all = distill_all; p.w_kd = w_kd; p.w_ce = w_ce;
+
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(KL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(cs);
+  int max_clusters = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_fused_kernel, &cfg);
+  if (e != cudaSuccess || max_clusters <= 0) { (void)cudaGetLastError(); max_clusters = lmod_num_sms() / cs; }
+  int64_t ncl = n_rows < max_clusters ? n_rows : max_clusters;
+  cfg.gridDim = dim3((unsigned)(ncl * cs));
+  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_fused_kernel, p));
+  lmod_count_launch();
+  return LMOD_OK;
+}

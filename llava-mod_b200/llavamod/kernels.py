@@ -1,0 +1,535 @@
+"""Torch-facing wrappers (``torch.autograd.Function``) around the C ABI of liblmod_b200.so.
+
+Each wrapper cites the reference call site it stands in for.  Tensors are bf16 CUDA, contiguous; fp32 only
+where the reference keeps fp32 (router gate, loss scalars, optimizer state).  No CPU fallback.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _C
+from ._C import call, ptr
+
+BF16 = torch.bfloat16
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _C.LmodError("llavamod kernels need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM plumbing.  Plain library GEMMs (cuBLAS through torch) for the dense contractions; every fused /
+# irregular op around them is one of our kernels.
+# ---------------------------------------------------------------------------------------------------
+def mm_nt(x, w, bias=None):
+    """y[M,N] = x[M,K] @ w[N,K]^T (+bias) -- nn.Linear forward."""
+    return torch.nn.functional.linear(x, w, bias)
+
+
+def mm_nn(dy, w):
+    """dx[M,K] = dy[M,N] @ w[N,K] -- nn.Linear dgrad."""
+    return dy @ w
+
+
+def mm_tn_acc(dy, x, grad):
+    """grad[N,K] += dy[M,N]^T @ x[M,K] -- nn.Linear wgrad accumulated in place into the flat grad buffer."""
+    if grad.dtype == dy.dtype:
+        grad.addmm_(dy.t(), x)
+    else:
+        grad.add_(dy.t() @ x)
+
+
+class LinearFn(Function):
+    """nn.Linear (modeling_qwen2.py:678-680,726,199-200; CLIP / projector linears).  ``wgrad``/``bgrad`` are views
+    of the flat gradient buffer (None when the parameter is frozen); wgrad is accumulated in place."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, wgrad, bgrad):
+        _need_cuda(x, w)
+        ctx.save_for_backward(x, w)
+        ctx.wgrad, ctx.bgrad = wgrad, bgrad
+        return mm_nt(x, w, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy2 = _c(dy).reshape(-1, dy.shape[-1])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = mm_nn(dy2, w).reshape(x.shape)
+        if ctx.wgrad is not None:
+            mm_tn_acc(dy2, x.reshape(-1, x.shape[-1]), ctx.wgrad)
+        if ctx.bgrad is not None:
+            ctx.bgrad.add_(dy2.sum(0).to(ctx.bgrad.dtype))
+        return dx, None, None, None, None
+
+
+def linear(x, w, bias=None, wgrad=None, bgrad=None):
+    if torch.is_grad_enabled() and (x.requires_grad or wgrad is not None):
+        return LinearFn.apply(x, w, bias, wgrad, bgrad)
+    return mm_nt(x, w, bias)
+
+
+# ---------------------------------------------------------------------------------------------------
+# norms / rope / activations
+# ---------------------------------------------------------------------------------------------------
+class RMSNormFn(Function):
+    """Qwen2RMSNorm (modeling_qwen2.py:105-110) with the decoder layer's residual add fused in
+    (modeling_qwen2.py:796,808 / llava_qwen1_5_moe.py:156,167).  Returns (normed, residual_stream)."""
+
+    @staticmethod
+    def forward(ctx, x, res, w, eps):
+        _need_cuda(x, w)
+        x = _c(x)
+        H = x.shape[-1]
+        rows = x.numel() // H
+        y = torch.empty_like(x)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        if res is not None:
+            res = _c(res)
+            s = torch.empty_like(x)
+            call("lmod_rmsnorm_fwd", ptr(x), ptr(res), ptr(w), rows, H, eps, ptr(y), ptr(s), ptr(rstd))
+        else:
+            s = x
+            call("lmod_rmsnorm_fwd", ptr(x), None, ptr(w), rows, H, eps, ptr(y), None, ptr(rstd))
+        ctx.save_for_backward(s, w, rstd)
+        ctx.had_res = res is not None
+        if res is None:
+            return y, x.new_empty(0)
+        return y, s
+
+    @staticmethod
+    def backward(ctx, dy, ds):
+        s, w, rstd = ctx.saved_tensors
+        H = s.shape[-1]
+        rows = s.numel() // H
+        dy = _c(dy)
+        dsp = None
+        if ctx.had_res and ds is not None:
+            dsp = ptr(_c(ds))
+        dx = torch.empty_like(s)
+        call("lmod_rmsnorm_bwd", ptr(dy), ptr(s), ptr(w), ptr(rstd), dsp, rows, H, ptr(dx))
+        return dx, (dx if ctx.had_res else None), None, None
+
+
+def rmsnorm(x, w, eps, res=None):
+    """-> (y, stream) where stream = x + res (or x).  Without autograd the kernel is called directly."""
+    if torch.is_grad_enabled() and (x.requires_grad or (res is not None and res.requires_grad)):
+        y, s = RMSNormFn.apply(x, res, w, eps)
+        return y, (s if res is not None else x)
+    x = _c(x)
+    H = x.shape[-1]
+    rows = x.numel() // H
+    y = torch.empty_like(x)
+    if res is not None:
+        s = torch.empty_like(x)
+        call("lmod_rmsnorm_fwd", ptr(x), ptr(_c(res)), ptr(w), rows, H, eps, ptr(y), ptr(s), None)
+        return y, s
+    call("lmod_rmsnorm_fwd", ptr(x), None, ptr(w), rows, H, eps, ptr(y), None, None)
+    return y, x
+
+
+def layernorm(x, w, b, eps):
+    """CLIP LayerNorm (transformers CLIPVisionModel via clip_encoder.py:54); frozen tower: forward only."""
+    x = _c(x)
+    H = x.shape[-1]
+    y = torch.empty_like(x)
+    call("lmod_layernorm_fwd", ptr(x), ptr(w), ptr(b), x.numel() // H, H, eps, ptr(y))
+    return y
+
+
+class RopeFn(Function):
+    """apply_rotary_pos_emb (modeling_qwen2.py:159-184) in place on the fused QKV projection output
+    [rows, (nh + 2*nkv)*hd]: q heads first, then k heads, then v."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, pos, nh, nkv, hd):
+        rows = qkv.numel() // qkv.shape[-1]
+        ld = qkv.shape[-1]
+        call("lmod_rope", ptr(qkv), ld, nh, qkv.data_ptr() + nh * hd * 2, ld, nkv, hd, ptr(cos), ptr(sin), ptr(pos), rows, 0)
+        ctx.mark_dirty(qkv)
+        ctx.save_for_backward(cos, sin, pos)
+        ctx.dims = (nh, nkv, hd)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, d):
+        cos, sin, pos = ctx.saved_tensors
+        nh, nkv, hd = ctx.dims
+        d = d.contiguous().clone()
+        rows = d.numel() // d.shape[-1]
+        ld = d.shape[-1]
+        call("lmod_rope", ptr(d), ld, nh, d.data_ptr() + nh * hd * 2, ld, nkv, hd, ptr(cos), ptr(sin), ptr(pos), rows, 1)
+        return d, None, None, None, None, None, None
+
+
+def rope_(qkv, cos, sin, pos, nh, nkv, hd):
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        return RopeFn.apply(qkv, cos, sin, pos, nh, nkv, hd)
+    rows = qkv.numel() // qkv.shape[-1]
+    ld = qkv.shape[-1]
+    call("lmod_rope", ptr(qkv), ld, nh, qkv.data_ptr() + nh * hd * 2, ld, nkv, hd, ptr(cos), ptr(sin), ptr(pos), rows, 0)
+    return qkv
+
+
+class SiluMulFn(Function):
+    """act_fn(gate_proj(x)) * up_proj(x) (modeling_qwen2.py:199-200) on the fused [rows, 2I] gate|up GEMM output."""
+
+    @staticmethod
+    def forward(ctx, gu):
+        gu = _c(gu)
+        I = gu.shape[-1] // 2
+        rows = gu.numel() // gu.shape[-1]
+        out = torch.empty(gu.shape[:-1] + (I,), dtype=gu.dtype, device=gu.device)
+        call("lmod_silu_mul_fwd", ptr(gu), 2 * I, rows, I, ptr(out))
+        ctx.save_for_backward(gu)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        (gu,) = ctx.saved_tensors
+        I = gu.shape[-1] // 2
+        rows = gu.numel() // gu.shape[-1]
+        dgu = torch.empty_like(gu)
+        call("lmod_silu_mul_bwd", ptr(_c(d)), ptr(gu), 2 * I, rows, I, ptr(dgu))
+        return dgu
+
+
+def silu_mul(gu):
+    if torch.is_grad_enabled() and gu.requires_grad:
+        return SiluMulFn.apply(gu)
+    gu = _c(gu)
+    I = gu.shape[-1] // 2
+    out = torch.empty(gu.shape[:-1] + (I,), dtype=gu.dtype, device=gu.device)
+    call("lmod_silu_mul_fwd", ptr(gu), 2 * I, gu.numel() // gu.shape[-1], I, ptr(out))
+    return out
+
+
+def silu_mul_bwd(d, gu):
+    I = gu.shape[-1] // 2
+    dgu = torch.empty_like(gu)
+    call("lmod_silu_mul_bwd", ptr(_c(d)), ptr(gu), 2 * I, gu.numel() // gu.shape[-1], I, ptr(dgu))
+    return dgu
+
+
+ACT_GELU, ACT_QUICK_GELU, ACT_NONE = 0, 1, 2
+
+
+def bias_act(x, bias, act):
+    x = _c(x)
+    n = x.shape[-1]
+    y = torch.empty_like(x)
+    call("lmod_bias_act_fwd", ptr(x), ptr(bias), x.numel() // n, n, act, ptr(y))
+    return y
+
+
+class GeluFn(Function):
+    """nn.GELU() of the mlp2x_gelu projector (multimodal_projector/builder.py:57-61)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        return bias_act(x, None, ACT_GELU)
+
+    @staticmethod
+    def backward(ctx, d):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("lmod_gelu_bwd", ptr(_c(d)), ptr(x), x.numel(), ptr(dx))
+        return dx
+
+
+def gelu(x):
+    if torch.is_grad_enabled() and x.requires_grad:
+        return GeluFn.apply(x)
+    return bias_act(x, None, ACT_GELU)
+
+
+# ---------------------------------------------------------------------------------------------------
+# multimodal splice (llava_arch.py:228-320): the integer plan is built on the host (see llava_arch.py in this
+# package); the device part is one gather kernel and, backwards, one scatter into the projector output grads.
+# ---------------------------------------------------------------------------------------------------
+class SpliceFn(Function):
+    @staticmethod
+    def forward(ctx, feats, embed_w, src, img_index, n_patches):
+        B, T = src.shape
+        H = embed_w.shape[1]
+        out = torch.empty(B, T, H, dtype=embed_w.dtype, device=embed_w.device)
+        call("lmod_splice_embed", ptr(embed_w), ptr(feats) if feats is not None else None, ptr(src), ptr(img_index),
+             B * T, H, n_patches, ptr(out))
+        ctx.save_for_backward(src, img_index)
+        ctx.fshape = feats.shape
+        ctx.n_patches = n_patches
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        src, img_index = ctx.saved_tensors
+        dfeats = torch.zeros(ctx.fshape, dtype=d.dtype, device=d.device)
+        B, T = src.shape
+        call("lmod_splice_embed_bwd", ptr(_c(d)), ptr(src), ptr(img_index), B * T, d.shape[-1], ctx.n_patches, ptr(dfeats))
+        return dfeats, None, None, None, None
+
+
+def splice_embed(feats, embed_w, src, img_index, n_patches):
+    feats = _c(feats)
+    if torch.is_grad_enabled() and feats.requires_grad:
+        return SpliceFn.apply(feats, embed_w, src, img_index, n_patches)
+    B, T = src.shape
+    H = embed_w.shape[1]
+    out = torch.empty(B, T, H, dtype=embed_w.dtype, device=embed_w.device)
+    call("lmod_splice_embed", ptr(embed_w), ptr(feats), ptr(src), ptr(img_index), B * T, H, n_patches, ptr(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# MoE layer (DeepSpeed 0.9.5 MoE; call site llava_qwen1_5_moe.py:536-546)
+# ---------------------------------------------------------------------------------------------------
+_sync_ws = {}
+
+
+def _grid_ws(device):
+    ws = _sync_ws.get(device)
+    if ws is None:
+        ws = torch.zeros(4, dtype=torch.int32, device=device)
+        _sync_ws[device] = ws
+    return ws
+
+
+def moe_capacity(S, E, capacity_factor, min_capacity):
+    return int(_C.lib().lmod_moe_capacity(S, E, float(capacity_factor), int(min_capacity)))
+
+
+def moe_route_scatter(x, wg, noise, capacity_factor, min_capacity, padded=True):
+    """One cooperative launch: fp32 gate GEMV, softmax, top-1 / Gumbel top-2, stable capacity positions,
+    renormalised weights, l_aux, expert offsets and the token scatter.  Returns a dict of device tensors."""
+    _need_cuda(x, wg, noise)
+    S, H = x.shape
+    E = wg.shape[0]
+    C = moe_capacity(S, E, capacity_factor, min_capacity)
+    dev = x.device
+    r = dict(
+        logits=torch.empty(S, E, dtype=torch.float32, device=dev), gates=torch.empty(S, E, dtype=torch.float32, device=dev),
+        idx=torch.empty(S, 2, dtype=torch.int32, device=dev), row=torch.empty(S, 2, dtype=torch.int32, device=dev),
+        w=torch.empty(S, 2, dtype=torch.float32, device=dev), offsets=torch.empty(E + 1, dtype=torch.int32, device=dev),
+        meta=torch.empty(4 + E, dtype=torch.float32, device=dev), capacity=C)
+    rows = E * C if padded else 2 * S
+    r["xp"] = torch.zeros(rows, H, dtype=x.dtype, device=dev) if padded else torch.empty(rows, H, dtype=x.dtype, device=dev)
+    cf = -float(capacity_factor) if padded else float(capacity_factor)
+    call("lmod_moe_route_scatter", ptr(x), ptr(wg), ptr(noise), S, H, E, cf, int(min_capacity), ptr(r["logits"]), ptr(r["gates"]),
+         ptr(r["idx"]), ptr(r["row"]), ptr(r["w"]), ptr(r["offsets"]), ptr(r["meta"]), ptr(r["xp"]), ptr(_grid_ws(dev)))
+    return r
+
+
+def moe_gather_combine(y, row, w, residual=None):
+    S = row.shape[0]
+    H = y.shape[-1]
+    out = torch.empty(S, H, dtype=y.dtype, device=y.device)
+    call("lmod_moe_gather_combine", ptr(y), ptr(row), ptr(w), ptr(residual) if residual is not None else None, S, H, ptr(out))
+    return out
+
+
+class MoEFn(Function):
+    """x: post-attention-layernorm hidden [S,H]; res: residual stream [S,H].  Experts are SwiGLU MLPs with fused
+    gate|up weights w_gu [E,2I,H] and w_dn [E,H,I].  Capacity-padded [E,C,*] slabs feed batched library GEMMs.
+    Returns (res + moe_out, l_aux)."""
+
+    @staticmethod
+    def forward(ctx, x, res, wg, w_gu, w_dn, noise, cf, min_cap, grads):
+        x = _c(x)
+        res = _c(res)
+        E, I2, H = w_gu.shape
+        r = moe_route_scatter(x, wg, noise, cf, min_cap, padded=True)
+        C = r["capacity"]
+        xp = r["xp"].view(E, C, H)
+        h1 = torch.bmm(xp, w_gu.transpose(1, 2))                       # [E,C,2I]
+        act = silu_mul(h1.detach())                                    # [E,C,I]
+        y = torch.bmm(act, w_dn.transpose(1, 2))                       # [E,C,H]
+        out = moe_gather_combine(y.view(E * C, H), r["row"], r["w"], res)
+        ctx.save_for_backward(x, wg, w_gu, w_dn, r["xp"], h1, act, y, r["row"], r["w"], r["gates"], r["idx"], r["meta"])
+        ctx.grads = grads
+        ctx.C = C
+        ctx.route = r
+        return out, r["meta"][0].clone()
+
+    @staticmethod
+    def backward(ctx, dout, dlaux):
+        x, wg, w_gu, w_dn, xp, h1, act, y, row, w, gates, idx, meta = ctx.saved_tensors
+        E, I2, H = w_gu.shape
+        C = ctx.C
+        S = x.shape[0]
+        dout = _c(dout)
+        dy = torch.zeros(E * C, H, dtype=dout.dtype, device=dout.device)
+        dw = torch.empty(S, 2, dtype=torch.float32, device=dout.device)
+        call("lmod_moe_combine_bwd", ptr(dout), ptr(y), ptr(row), ptr(w), S, H, ptr(dy), ptr(dw))
+        dy3 = dy.view(E, C, H)
+        g = ctx.grads
+        dact = torch.bmm(dy3, w_dn)                                    # [E,C,I]
+        if g is not None and g.get("w_dn") is not None:
+            g["w_dn"].baddbmm_(dy3.transpose(1, 2), act)               # [E,H,I] +=
+        dh1 = silu_mul_bwd(dact, h1)
+        dxp = torch.bmm(dh1, w_gu)                                     # [E,C,H]
+        if g is not None and g.get("w_gu") is not None:
+            g["w_gu"].baddbmm_(dh1.transpose(1, 2), xp.view(E, C, H))
+        dlogits = torch.empty(S, E, dtype=torch.float32, device=dout.device)
+        gl = None
+        if dlaux is not None:
+            gl = dlaux.to(torch.float32).reshape(1).contiguous()
+        call("lmod_moe_gate_bwd", ptr(gates), ptr(idx), ptr(row), ptr(dw), ptr(meta), ptr(gl) if gl is not None else None, S, E, ptr(dlogits))
+        dx = torch.empty_like(x)
+        call("lmod_moe_scatter_bwd", ptr(dxp), ptr(row), ptr(dlogits), ptr(wg), None, S, H, E, ptr(dx))
+        if g is not None and g.get("wg") is not None:
+            ws = torch.empty(32, E, H, dtype=torch.float32, device=dout.device)
+            call("lmod_moe_wg_grad", ptr(x), ptr(dlogits), S, H, E, ptr(ws), ptr(g["wg"]))
+        return dx, dout, None, None, None, None, None, None, None
+
+
+def moe_forward_nograd(x, res, wg, w_gu, w_dn, noise, cf, min_cap):
+    E, I2, H = w_gu.shape
+    r = moe_route_scatter(_c(x), wg, noise, cf, min_cap, padded=True)
+    C = r["capacity"]
+    h1 = torch.bmm(r["xp"].view(E, C, H), w_gu.transpose(1, 2))
+    act = silu_mul(h1)
+    y = torch.bmm(act, w_dn.transpose(1, 2))
+    return moe_gather_combine(y.view(E * C, H), r["row"], r["w"], _c(res)), r["meta"][0].clone(), r
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused lm_head + mimic-KL (+ shifted CE) loss head
+# ---------------------------------------------------------------------------------------------------
+def kl_fused(s_logits, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all=False, dlogits=None):
+    """Raw kernel call.  s_logits/t_logits [N,ld] bf16, labels [N] int64.  Returns (out4, row_out).
+    out4 = {align_loss, ce_loss, n_kd, n_ce}.  dlogits (may alias s_logits) receives the gradient."""
+    _need_cuda(s_logits, t_logits, labels)
+    N = labels.numel()
+    dev = s_logits.device
+    counts = torch.empty(2, dtype=torch.float32, device=dev)
+    row_out = torch.empty(N, 4, dtype=torch.float32, device=dev)
+    out4 = torch.empty(4, dtype=torch.float32, device=dev)
+    da = 1 if distill_all else 0
+    call("lmod_kl_counts", ptr(labels), N, seq_len, da, ptr(counts))
+    call("lmod_kl_fwd_bwd", ptr(s_logits), s_logits.stride(0), ptr(t_logits), t_logits.stride(0), ptr(labels), N, seq_len, vocab, da,
+         float(w_kd), float(w_ce), ptr(counts), ptr(row_out), ptr(dlogits) if dlogits is not None else None,
+         dlogits.stride(0) if dlogits is not None else 0)
+    call("lmod_kl_finalize", ptr(row_out), ptr(labels), N, seq_len, da, ptr(out4))
+    return out4, row_out
+
+
+class DistillHeadFn(Function):
+    """lm_head GEMM (llava_qwen1_5_moe.py:407-408) + get_logp / compute_align_loss against the teacher's logits
+    (align_trainer.py:497-528) + the model's shifted CE (llava_qwen1_5_moe.py:413-421), forward and backward in one
+    sweep over the vocabulary.  Returns (w_kd*align + w_ce*ce, align, ce); only the first is differentiable."""
+
+    @staticmethod
+    def forward(ctx, hidden, w_head, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all, head_grad):
+        h2 = _c(hidden).reshape(-1, hidden.shape[-1])
+        logits = mm_nt(h2, w_head)                                      # [N, Vs] bf16
+        if logits.shape[1] != vocab and w_ce != 0.0:
+            raise _C.LmodError("fused CE needs student vocab == kd vocab slice")
+        out4, _ = kl_fused(logits, t_logits, labels.reshape(-1), seq_len, vocab, w_kd, w_ce, distill_all, dlogits=logits)
+        if logits.shape[1] > vocab:
+            logits[:, vocab:].zero_()
+        ctx.save_for_backward(logits, w_head, h2)
+        ctx.hshape = hidden.shape
+        ctx.head_grad = head_grad
+        align, ce = out4[0], out4[1]
+        total = w_kd * align + (w_ce * ce if w_ce != 0.0 else 0.0)
+        ctx.mark_non_differentiable(align, ce)
+        return total, align, ce
+
+    @staticmethod
+    def backward(ctx, g, _a, _c2):
+        dlogits, w_head, h2 = ctx.saved_tensors
+        dh = mm_nn(dlogits, w_head)
+        dh = (dh * g.to(dh.dtype)).reshape(ctx.hshape)
+        if ctx.head_grad is not None:
+            ctx.head_grad.add_((dlogits.t() @ h2) * g.to(dlogits.dtype))
+        return dh, None, None, None, None, None, None, None, None, None
+
+
+def distill_head(hidden, w_head, t_logits, labels, vocab, w_kd, w_ce, distill_all=False, head_grad=None):
+    return DistillHeadFn.apply(hidden, w_head, t_logits, labels, labels.shape[-1], vocab, float(w_kd), float(w_ce), bool(distill_all), head_grad)
+
+
+# ---------------------------------------------------------------------------------------------------
+# DPO log-prob head (dpo_trainer.py:483-495)
+# ---------------------------------------------------------------------------------------------------
+def logp_gather(logits, labels, average=False):
+    """logits [B,T,V] bf16 (contiguous), labels [B,T] int64 -> (seq_logp [B], tok_logp [B*T], lse [B*T])."""
+    B, T, V = logits.shape
+    dev = logits.device
+    tok = torch.empty(B * T, dtype=torch.float32, device=dev)
+    lse = torch.empty(B * T, dtype=torch.float32, device=dev)
+    seq = torch.empty(B, dtype=torch.float32, device=dev)
+    call("lmod_logp_gather_fwd", ptr(logits), logits.stride(1), ptr(labels), B, T, V, ptr(tok), ptr(lse), ptr(seq), 1 if average else 0)
+    return seq, tok, lse
+
+
+class LogpHeadFn(Function):
+    """lm_head GEMM + DPOTrainer.get_logp; backward writes d logits in place and returns d hidden."""
+
+    @staticmethod
+    def forward(ctx, hidden, w_head, labels, head_grad):
+        B, T, H = hidden.shape
+        logits = mm_nt(_c(hidden).reshape(-1, H), w_head).view(B, T, -1)
+        labels = _c(labels)
+        seq, tok, lse = logp_gather(logits, labels)
+        ctx.save_for_backward(logits, w_head, labels, lse, hidden)
+        ctx.head_grad = head_grad
+        return seq
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, w_head, labels, lse, hidden = ctx.saved_tensors
+        B, T, V = logits.shape
+        g = _c(g.to(torch.float32))
+        call("lmod_logp_gather_bwd", ptr(logits), logits.stride(1), ptr(labels), B, T, V, ptr(lse), ptr(g), 0, ptr(logits), logits.stride(1))
+        d2 = logits.view(B * T, V)
+        dh = mm_nn(d2, w_head).view(hidden.shape)
+        if ctx.head_grad is not None:
+            ctx.head_grad.add_(d2.t() @ hidden.reshape(B * T, -1))
+        return dh, None, None, None
+
+
+def logp_head(hidden, w_head, labels, head_grad=None):
+    return LogpHeadFn.apply(hidden, w_head, labels, head_grad)
+
+
+# ---------------------------------------------------------------------------------------------------
+# API-compat materialising forms (AlignTrainer.get_p / get_logp / compute_align_loss signatures)
+# ---------------------------------------------------------------------------------------------------
+def softmax_rows(logits_bf16, vocab, log_mode):
+    x = _c(logits_bf16)
+    V = x.shape[-1]
+    n = x.numel() // V
+    out = torch.empty(x.shape[:-1] + (vocab,), dtype=torch.float32, device=x.device)
+    call("lmod_softmax_rows", ptr(x), V, n, vocab, 1 if log_mode else 0, ptr(out), vocab)
+    return out
+
+
+def align_loss_dense(logp, probs, labels, distill_all=False):
+    V = logp.shape[-1]
+    n = logp.numel() // V
+    row_x = torch.empty(n, dtype=torch.float32, device=logp.device)
+    out = torch.empty(1, dtype=torch.float32, device=logp.device)
+    call("lmod_align_loss_dense", ptr(_c(logp)), ptr(_c(probs)), V, ptr(_c(labels)), n, V, 1 if distill_all else 0, ptr(row_x), ptr(out))
+    return out[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# optimizer
+# ---------------------------------------------------------------------------------------------------
+def sumsq_(buf, out):
+    call("lmod_sumsq", ptr(buf), 1 if buf.dtype == torch.float32 else 0, buf.numel(), ptr(out))
+
+
+def adamw_(master, m, v, grad, model, lr, beta1, beta2, eps, wd, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
+    call("lmod_adamw", ptr(master), ptr(m), ptr(v), ptr(grad), 1 if grad.dtype == torch.float32 else 0,
+         ptr(model) if model is not None else None, master.numel(), float(lr), float(beta1), float(beta2), float(eps), float(wd),
+         int(step), ptr(gnorm_sq) if gnorm_sq is not None else None, float(max_norm), float(grad_scale))

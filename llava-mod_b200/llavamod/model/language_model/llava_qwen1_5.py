@@ -1,0 +1,17 @@
+"""Dense LLaVA-Qwen1_5 wrapper (teacher, or dense student of the dense->dense stage).
+Reference: llavamod/model/language_model/llava_qwen1_5.py (LlavaQwen1_5Config / LlavaQwen1_5Model / LlavaQwen1_5ForCausalLM)."""
+from .llava_qwen_common import LlavaQwenForCausalLMBase, LlavaQwenModelBase
+from .qwen2_core import Qwen2Config
+
+
+class LlavaQwen1_5Config(Qwen2Config):
+    model_type = "llava_qwen1_5"
+
+
+class LlavaQwen1_5Model(LlavaQwenModelBase):
+    config_class = LlavaQwen1_5Config
+
+
+class LlavaQwen1_5ForCausalLM(LlavaQwenForCausalLMBase):
+    config_class = LlavaQwen1_5Config
+    model_class = LlavaQwen1_5Model

@@ -1,0 +1,182 @@
+"""AlignTrainer -- mimic distillation (teacher-weighted CE over the vocabulary, "KL") of a sparse-MoE student.
+
+Reference: llavamod/train/align_trainer.py (AlignTrainer :180; get_p :455-477; get_logp :479-501; compute_align_loss
+:503-528; compute_loss :530-594; store_metrics/log :596-614).  Semantics kept: un-shifted mask, hard-coded vocabulary
+slice 151936, ``moe_loss`` counted inside the model loss AND again by the trainer under ``kd_lm``, ``-1.0`` sentinel metric,
+0/0 -> NaN for a fully masked batch.
+
+B200 hot loop (``compute_loss``): frozen teacher forward (no grad) -> bf16 teacher logits; student forward; the student's
+lm_head GEMM output goes straight into ONE fused kernel that produces the mimic loss, the LM loss and d(logits) in a single
+sweep (no fp32 [N,V] probability tensors -- the reference materialises five of them); when teacher and student hold the
+same frozen CLIP tower it runs once per micro-batch instead of twice.
+"""
+from collections import defaultdict
+from typing import Any, Dict, Literal, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from ..constants import IGNORE_INDEX, KD_VOCAB_SIZE
+from ..model.utils import create_reference_model, disable_dropout_in_model
+from .trainer_base import BaseTrainer
+
+
+class _Wrapped:
+    """Gives a bare module the ``.module`` attribute the reference dereferences on the DeepSpeed-wrapped teacher
+    (align_trainer.py:305,309); the build accepts wrapped and bare teachers."""
+
+    def __init__(self, module):
+        self.module = module
+
+    def __call__(self, *a, **kw):
+        return self.module(*a, **kw)
+
+    def __getattr__(self, k):
+        return getattr(self.module, k)
+
+
+def same_frozen_tower(a, b):
+    ta, tb = a.get_image_tower(), b.get_image_tower()
+    if ta is None or tb is None or not (ta.is_loaded and tb.is_loaded):
+        return False
+    sa, sb = ta.state_dict(), tb.state_dict()
+    if sa.keys() != sb.keys() or any(p.requires_grad for p in ta.parameters()) or any(p.requires_grad for p in tb.parameters()):
+        return False
+    return ta.select_layer == tb.select_layer and all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+class AlignTrainer(BaseTrainer):
+    def __init__(self, model=None, ref_model=None, args=None, data_collator=None, train_dataset=None, eval_dataset=None,
+                 tokenizer=None, label_pad_token_id: int = -100, padding_value: int = 0, beta: float = 0.1,
+                 label_smoothing: float = 0, loss_type: str = "sigmoid", moe_loss_enable: bool = False,
+                 disable_dropout: bool = True, model_init=None, compute_metrics=None, callbacks=None,
+                 optimizers=(None, None), preprocess_logits_for_metrics=None):
+        if ref_model:
+            self.ref_model = ref_model
+        else:
+            self.ref_model = create_reference_model(model)
+        if disable_dropout:
+            disable_dropout_in_model(model)
+            disable_dropout_in_model(self.ref_model.module if hasattr(self.ref_model, "module") else self.ref_model)
+        self.label_pad_token_id = label_pad_token_id
+        self.padding_value = padding_value
+        self.beta = beta
+        self.label_smoothing = label_smoothing
+        self.loss_type = loss_type
+        self.moe_loss_enable = moe_loss_enable
+        self._stored_metrics = defaultdict(lambda: defaultdict(list))
+        super().__init__(model=model, args=args, data_collator=data_collator, train_dataset=train_dataset,
+                         eval_dataset=eval_dataset, tokenizer=tokenizer, model_init=model_init,
+                         compute_metrics=compute_metrics, callbacks=callbacks, optimizers=optimizers,
+                         preprocess_logits_for_metrics=preprocess_logits_for_metrics)
+        if not hasattr(self.ref_model, "module"):
+            self.ref_model = _Wrapped(self.ref_model)
+        self.ref_model.module.eval()
+        for p in self.ref_model.module.parameters():
+            p.requires_grad = False
+        self.share_tower = same_frozen_tower(self.model, self.ref_model.module)
+        self.kd_vocab = KD_VOCAB_SIZE
+
+    # ---- API-compat pieces (materialising forms, our kernels) ------------------------------------------------
+    def _moe_loss_of(self, outputs):
+        if getattr(self.args, "moe_enable", False) and self.moe_loss_enable and getattr(outputs, "moe_loss", None) is not None:
+            return outputs.moe_loss
+        return None
+
+    def get_p(self, model, inputs):
+        """align_trainer.py:455-477 -> (softmax(logits[:, :, :151936]) fp32, sft_loss, moe_loss)"""
+        outputs = model(**inputs, return_dict=True)
+        logits, labels = outputs.logits, outputs.labels
+        if logits.shape[:-1] != labels.shape:
+            raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+        v = min(self.kd_vocab, logits.shape[-1])
+        probs = K.softmax_rows(logits.to(torch.bfloat16), v, log_mode=False)
+        return probs, outputs.loss, self._moe_loss_of(outputs)
+
+    def get_logp(self, model, inputs):
+        """align_trainer.py:479-501 -> (log_softmax fp32, sft_loss, moe_loss, labels).  Forward-only values; the training
+        path is ``compute_loss`` (fused)."""
+        outputs = model(**inputs, return_dict=True)
+        logits, labels = outputs.logits, outputs.labels
+        if logits.shape[:-1] != labels.shape:
+            raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+        v = min(self.kd_vocab, logits.shape[-1])
+        logprobs = K.softmax_rows(logits.to(torch.bfloat16), v, log_mode=True)
+        return logprobs, outputs.loss, self._moe_loss_of(outputs), labels
+
+    def compute_align_loss(self, policy_logprobs, reference_probs, labels):
+        """align_trainer.py:503-528 on materialised fp32 tensors."""
+        return K.align_loss_dense(policy_logprobs, reference_probs, labels, bool(getattr(self.args, "distill_all_tokens", False)))
+
+    # ---- the hot loop body ---------------------------------------------------------------------------------------
+    def compute_loss(self, model, inputs: Dict[str, Union[torch.Tensor, Any]], return_outputs=False):
+        assert self.ref_model is not None, "ref model can not be none!"
+        ref = self.ref_model.module
+        images = inputs.get("images", None)
+        fwd = dict(input_ids=inputs["input_ids"], labels=inputs["labels"], attention_mask=inputs.get("attention_mask"), images=images)
+        tower_feats = None
+        with torch.no_grad():
+            if self.share_tower and images is not None:
+                dev = model.device
+                imgs = torch.stack([im.to(dev, non_blocking=True) for im in images]) if not torch.is_tensor(images) else images.to(dev)
+                fwd["images"] = imgs
+                tower_feats = model.get_image_tower()(imgs.to(model.dtype))
+            t = ref.forward_hidden(**fwd, tower_features=tower_feats)
+            th = t["hidden"]
+            t_logits = K.mm_nt(th.reshape(-1, th.shape[-1]), ref.lm_head.weight)              # teacher logits, bf16 [N, Vt]
+        s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"))
+        labels = s["labels"]
+        if s["hidden"].shape[:2] != labels.shape or th.shape[:2] != labels.shape:
+            raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+        vocab = min(self.kd_vocab, model.config.vocab_size, t_logits.shape[-1])
+        w_ce = 0.0 if self.loss_type == "only_kd" else 1.0
+        total, align_loss, ce = K.distill_head(s["hidden"], model.lm_head.weight, t_logits, labels, vocab, 1.0, w_ce,
+                                               bool(getattr(self.args, "distill_all_tokens", False)), model.lm_head_grad)
+        model_moe_loss = model.moe_loss_from(s["l_aux"]) if getattr(model, "is_moe", False) else None
+        # model.loss = CE (+ moe_loss)   llava_qwen1_5_moe.py:421,434
+        policy_sft_loss = ce if model_moe_loss is None else ce + model_moe_loss.detach()
+        losses = total
+        if w_ce != 0.0 and model_moe_loss is not None:
+            losses = losses + model_moe_loss                       # the moe_loss already inside the model's loss
+        policy_moe_loss = model_moe_loss if (getattr(self.args, "moe_enable", False) and self.moe_loss_enable) else None
+        if policy_moe_loss is not None:                             # `if policy_moe_loss:` -- l_aux > 0 always; no host sync here
+            moe_loss = policy_moe_loss
+            losses = losses + moe_loss                              # ... and counted again by the trainer (align_trainer.py:575-577)
+        else:
+            moe_loss = torch.full_like(align_loss, -1.0)
+        outputs = {"loss": losses.detach().mean(), "loss/align": align_loss.detach().mean(),
+                   "loss/moe_balance": moe_loss.detach().mean(), "loss/lm": policy_sft_loss.detach().mean()}
+        self.store_metrics(outputs, train_eval="train")
+        if return_outputs:
+            return losses.mean(), outputs
+        return losses.mean()
+
+    def store_metrics(self, metrics: Dict[str, float], train_eval: Literal["train", "eval"] = "train") -> None:
+        for key, value in metrics.items():
+            self._stored_metrics[train_eval][key].append(value)
+
+    def log(self, logs: Dict[str, float]) -> None:
+        train_eval = "train" if "loss" in logs else "eval"
+        for key, metrics in self._stored_metrics[train_eval].items():
+            logs[key] = torch.stack([torch.as_tensor(m, dtype=torch.float32).detach().cpu() for m in metrics]).mean().item()
+        del self._stored_metrics[train_eval]
+        return super().log(logs)
+
+    def _save_checkpoint(self, model, trial, metrics=None):
+        if getattr(self.args, "tune_mm_mlp_adapter", False):        # adaptor-only checkpoints (align_trainer.py:616-633)
+            import os
+            d = os.path.join(self._get_output_dir(trial), f"checkpoint-{self.state.global_step}")
+            if self.rank == 0:
+                os.makedirs(d, exist_ok=True)
+                self.model.config.save_pretrained(d)
+                w = {k: v.detach().cpu() for k, v in self.model.state_dict().items() if "mm_projector" in k}
+                torch.save(w, os.path.join(d, "mm_projector.bin"))
+        else:
+            super()._save_checkpoint(model, trial, metrics)
+
+    def _save(self, output_dir: Optional[str] = None, state_dict=None):
+        if getattr(self.args, "tune_mm_mlp_adapter", False):
+            pass
+        else:
+            super()._save(output_dir, state_dict)

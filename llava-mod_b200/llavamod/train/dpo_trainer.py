@@ -1,0 +1,147 @@
+"""DPOTrainer -- preference distillation (DPO / IPO / hinge / KTO-pair on sequence log-prob ratios).
+
+Reference: llavamod/train/dpo_trainer.py (DPOTrainer :180; get_logp :462-495; dpo_loss :497-562; compute_loss :564-641).
+Kept: shift by one, NO vocabulary slice, masked sequence SUM of gathered log-probs, the four loss types with beta=0.1,
+``chosen_moe + rejected_moe`` added when enabled, the ten logged metrics.
+
+B200 hot loop: two frozen-teacher forwards (no grad) and two student forwards; each lm_head GEMM feeds the fused
+log-softmax+gather kernel (online LSE + pick, 2*V bytes/token) instead of materialising log_softmax over [B,T,V]; the DPO
+scalar math runs on [B] device tensors; backward re-reads the bf16 logits once and writes d(logits) in place.
+"""
+from collections import defaultdict
+from typing import Any, Dict, Literal, Tuple, Union
+
+import torch
+import torch.nn.functional as F
+
+from .. import kernels as K
+from ..model.utils import create_reference_model, disable_dropout_in_model
+from .align_trainer import _Wrapped, same_frozen_tower
+from .trainer_base import BaseTrainer
+
+
+class DPOTrainer(BaseTrainer):
+    def __init__(self, model=None, ref_model=None, args=None, data_collator=None, train_dataset=None, eval_dataset=None,
+                 tokenizer=None, label_pad_token_id: int = -100, padding_value: int = 0, beta: float = 0.1,
+                 label_smoothing: float = 0, loss_type: str = "sigmoid", moe_loss_enable: bool = False,
+                 disable_dropout: bool = True, model_init=None, compute_metrics=None, callbacks=None,
+                 optimizers=(None, None), preprocess_logits_for_metrics=None):
+        self.ref_model = ref_model if ref_model else create_reference_model(model)
+        if disable_dropout:
+            disable_dropout_in_model(model)
+        self.label_pad_token_id = label_pad_token_id
+        self.padding_value = padding_value
+        self.beta = beta
+        self.label_smoothing = label_smoothing
+        self.loss_type = loss_type
+        self.moe_loss_enable = moe_loss_enable
+        self._stored_metrics = defaultdict(lambda: defaultdict(list))
+        super().__init__(model=model, args=args, data_collator=data_collator, train_dataset=train_dataset,
+                         eval_dataset=eval_dataset, tokenizer=tokenizer, model_init=model_init,
+                         compute_metrics=compute_metrics, callbacks=callbacks, optimizers=optimizers,
+                         preprocess_logits_for_metrics=preprocess_logits_for_metrics)
+        if not hasattr(self.ref_model, "module"):
+            self.ref_model = _Wrapped(self.ref_model)
+        self.ref_model.module.eval()
+        for p in self.ref_model.module.parameters():
+            p.requires_grad = False
+        self.share_tower = same_frozen_tower(self.model, self.ref_model.module)
+
+    def _seq_logp(self, model, fwd, tower_feats, noise=None, grad=True):
+        r = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=noise)
+        if r["hidden"].shape[:2] != r["labels"].shape:
+            raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+        if grad:
+            logps = K.logp_head(r["hidden"], model.lm_head.weight, r["labels"], model.lm_head_grad)
+        else:
+            h = r["hidden"]
+            logits = K.mm_nt(h.reshape(-1, h.shape[-1]), model.lm_head.weight).view(h.shape[0], h.shape[1], -1)
+            logps = K.logp_gather(logits, r["labels"].contiguous())[0]
+        return logps, r
+
+    def get_logp(self, model, inputs, average_log_prob: bool = False):
+        """dpo_trainer.py:462-495 -> (sequence log-probs [B], sft_loss, moe_loss).  API-compat form (runs the public forward)."""
+        outputs = model(**inputs, return_dict=True)
+        logits, labels = outputs.logits, outputs.labels
+        if logits.shape[:-1] != labels.shape:
+            raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+        seq = K.logp_gather(logits.to(torch.bfloat16).contiguous(), labels.contiguous(), average=average_log_prob)[0]
+        moe = outputs.moe_loss if (getattr(self.args, "moe_enable", False) and self.moe_loss_enable and getattr(outputs, "moe_loss", None) is not None) else None
+        return seq, outputs.loss, moe
+
+    def dpo_loss(self, policy_chosen_logps, policy_rejected_logps, reference_chosen_logps, reference_rejected_logps,
+                 reference_free: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """dpo_trainer.py:497-562 ([B]-sized device math; K18 is a trivial epilogue of K17)."""
+        pi_logratios = policy_chosen_logps - policy_rejected_logps
+        ref_logratios = 0 if reference_free else reference_chosen_logps - reference_rejected_logps
+        logits = pi_logratios - ref_logratios
+        if self.loss_type == "sigmoid":
+            losses = (-F.logsigmoid(self.beta * logits) * (1 - self.label_smoothing)
+                      - F.logsigmoid(-self.beta * logits) * self.label_smoothing)
+        elif self.loss_type == "hinge":
+            losses = torch.relu(1 - self.beta * logits)
+        elif self.loss_type == "ipo":
+            losses = (logits - 1 / (2 * self.beta)) ** 2
+        elif self.loss_type == "kto_pair":
+            chosen_KL = (policy_chosen_logps - reference_chosen_logps).mean().clamp(min=0)
+            rejected_KL = (policy_rejected_logps - reference_rejected_logps).mean().clamp(min=0)
+            chosen_logratios = policy_chosen_logps - reference_chosen_logps
+            rejected_logratios = policy_rejected_logps - reference_rejected_logps
+            losses = torch.cat((1 - torch.sigmoid(self.beta * (chosen_logratios - rejected_KL)),
+                                1 - torch.sigmoid(self.beta * (chosen_KL - rejected_logratios))), 0)
+        else:
+            raise ValueError(f"Unknown loss type: {self.loss_type}. Should be one of ['sigmoid', 'hinge']")
+        chosen_rewards = self.beta * (policy_chosen_logps - reference_chosen_logps).detach()
+        rejected_rewards = self.beta * (policy_rejected_logps - reference_rejected_logps).detach()
+        return losses, chosen_rewards, rejected_rewards
+
+    def compute_loss(self, model, inputs: Dict[str, Union[torch.Tensor, Any]], return_outputs=False):
+        assert self.ref_model is not None, "ref model can not be none!"
+        ref = self.ref_model.module
+        images = inputs.get("images", None)
+        tower_feats = None
+        if self.share_tower and images is not None:
+            with torch.no_grad():
+                dev = model.device
+                images = torch.stack([im.to(dev, non_blocking=True) for im in images]) if not torch.is_tensor(images) else images.to(dev)
+                tower_feats = model.get_image_tower()(images.to(model.dtype))                 # once instead of 4x (dpo_trainer.py:595-607)
+        ch = dict(input_ids=inputs["chosen_input_ids"], labels=inputs["chosen_labels"], attention_mask=inputs["chosen_attention_mask"], images=images)
+        rj = dict(input_ids=inputs["rejected_input_ids"], labels=inputs["rejected_labels"], attention_mask=inputs["rejected_attention_mask"], images=images)
+        with torch.no_grad():
+            reference_chosen_logps, _ = self._seq_logp(ref, ch, tower_feats, grad=False)
+            reference_rejected_logps, _ = self._seq_logp(ref, rj, tower_feats, grad=False)
+        noise = inputs.get("moe_noise") or (None, None)
+        policy_chosen_logps, rc = self._seq_logp(model, ch, tower_feats, noise[0])
+        policy_rejected_logps, rr = self._seq_logp(model, rj, tower_feats, noise[1])
+        reward_losses, chosen_rewards, rejected_rewards = self.dpo_loss(policy_chosen_logps, policy_rejected_logps,
+                                                                        reference_chosen_logps, reference_rejected_logps)
+        enabled = getattr(self.args, "moe_enable", False) and self.moe_loss_enable and getattr(model, "is_moe", False)
+        if enabled and len(rc["l_aux"]) and len(rr["l_aux"]):
+            moe_loss = model.moe_loss_from(rc["l_aux"]) + model.moe_loss_from(rr["l_aux"])
+            losses = reward_losses + moe_loss
+        else:
+            moe_loss = torch.full_like(reward_losses, -1.0)
+            losses = reward_losses
+        reward_accuracies = (chosen_rewards > rejected_rewards).float()
+        outputs = {"loss": losses.detach().mean(), "loss/reward": reward_losses.detach().mean(),
+                   "loss/moe_balance": moe_loss.detach().mean(),
+                   # the reference logs the chosen forward's LM loss; the fused path reports -mean token log-prob of the chosen response
+                   "loss/policy_chosen": (-policy_chosen_logps.detach()).mean(),
+                   "rewards/chosen": chosen_rewards.mean(), "rewards/rejected": rejected_rewards.mean(),
+                   "rewards/accuracies": reward_accuracies.mean(), "rewards/margins": (chosen_rewards - rejected_rewards).mean(),
+                   "logps/chosen": policy_chosen_logps.detach().mean(), "logps/rejected": policy_rejected_logps.detach().mean()}
+        self.store_metrics(outputs, train_eval="train")
+        if return_outputs:
+            return losses.mean(), outputs
+        return losses.mean()
+
+    def store_metrics(self, metrics: Dict[str, float], train_eval: Literal["train", "eval"] = "train") -> None:
+        for key, value in metrics.items():
+            self._stored_metrics[train_eval][key].append(value)
+
+    def log(self, logs: Dict[str, float]) -> None:
+        train_eval = "train" if "loss" in logs else "eval"
+        for key, metrics in self._stored_metrics[train_eval].items():
+            logs[key] = torch.stack([torch.as_tensor(m, dtype=torch.float32).detach().cpu() for m in metrics]).mean().item()
+        del self._stored_metrics[train_eval]
+        return super().log(logs)

@@ -1,0 +1,170 @@
+"""Training state for the data-parallel distillation step: flat parameter / gradient / optimizer arenas in HBM,
+fused AdamW, gradient all-reduce over NCCL.
+
+Replaces what the reference gets from HF Trainer + accelerate + DeepSpeed ZeRO-2 with CPU-offloaded Adam
+(llavamod/train/align_trainer.py:326-453, llavamod/config/dpconfig/zero2_offload.json): on a 180 GB B200 nothing is
+sharded or offloaded -- the trainable student parameters (0.5B-4E: 521 M) keep bf16 model copy + fp32 master + two fp32
+moments + a bf16 gradient buffer resident (16 B/param = 8.3 GB), the frozen teacher is replicated, and the only
+collective of a step is ONE all-reduce over the flat gradient buffer (student grads only).
+
+Layout: every trainable *storage unit* (a fused q|k|v / gate|up buffer, an [E,2I,H] expert stack, or a plain parameter)
+is packed into one contiguous bf16 arena (fp32 units -- the router ``wg`` -- into a second, tiny fp32 arena), each unit
+aligned to 256 bytes.  The ``nn.Parameter``s the reference exposes are re-pointed to views of the arena, their ``.grad``
+to views of the gradient arena, so the wgrad GEMMs accumulate straight into the buffer NCCL reduces.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from .. import kernels as K
+from ..model.language_model.qwen2_core import Experts, Qwen2Attention, Qwen2MLP
+
+ALIGN = 128  # elements
+
+
+def _units(model):
+    """Yields (storage_tensor, [member Parameters]) -- fused buffers first, then every remaining parameter."""
+    seen = set()
+    out = []
+
+    def add(storage, members):
+        members = [m for m in members if m is not None]
+        for m in members:
+            seen.add(id(m))
+        out.append((storage, members))
+
+    for mod in model.modules():
+        if isinstance(mod, Qwen2Attention):
+            add(mod.qkv_weight, [mod.q_proj.weight, mod.k_proj.weight, mod.v_proj.weight])
+            add(mod.qkv_bias, [mod.q_proj.bias, mod.k_proj.bias, mod.v_proj.bias])
+        elif isinstance(mod, Experts):
+            add(mod.gu_weight, [p for e in mod.deepspeed_experts for p in (e.gate_proj.weight, e.up_proj.weight)])
+            add(mod.dn_weight, [e.down_proj.weight for e in mod.deepspeed_experts])
+    for mod in model.modules():
+        if isinstance(mod, Qwen2MLP) and id(mod.gate_proj.weight) not in seen:
+            add(mod.gu_weight, [mod.gate_proj.weight, mod.up_proj.weight])
+    for p in model.parameters():
+        if id(p) not in seen:
+            add(p, [p])
+    return out
+
+
+class TrainState:
+    def __init__(self, model, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
+                 process_group=None):
+        self.model = model
+        self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.step_count = 0
+        dev = next(model.parameters()).device
+        u16, u32 = [], []
+        for storage, members in _units(model):
+            rg = [m.requires_grad for m in members]
+            if not any(rg):
+                continue
+            if not all(rg):
+                raise NotImplementedError("a fused buffer with mixed frozen/trainable members (e.g. only gate_proj of gate|up) "
+                                          "is not supported; train or freeze q/k/v and gate/up together")
+            (u32 if storage.dtype == torch.float32 else u16).append((storage, members))
+        self.n16 = self._pack(u16, torch.bfloat16, dev, "16")
+        self.n32 = self._pack(u32, torch.float32, dev, "32")
+        self.master = self.w16.float() if self.n16 else None
+        self.m16 = torch.zeros_like(self.master) if self.n16 else None
+        self.v16 = torch.zeros_like(self.master) if self.n16 else None
+        self.m32 = torch.zeros_like(self.w32) if self.n32 else None
+        self.v32 = torch.zeros_like(self.w32) if self.n32 else None
+        self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        gv = {}
+        for storage, g in self._views:
+            gv[id(storage)] = g
+        # hand the gradient views to the modules whose forward issues the wgrad GEMMs
+        core = model.get_model() if hasattr(model, "get_model") else model
+        core.grad_views = gv
+        if getattr(core, "mm_projector", None) is not None:
+            core.mm_projector.grad_views = gv
+        if hasattr(model, "lm_head") and id(model.lm_head.weight) in gv:
+            model.lm_head_grad = gv[id(model.lm_head.weight)]
+        self.num_trainable = self.n16 + self.n32
+
+    def _pack(self, units, dtype, dev, tag):
+        off, plan = 0, []
+        for storage, members in units:
+            plan.append((storage, members, off))
+            off += (storage.numel() + ALIGN - 1) // ALIGN * ALIGN
+        w = torch.zeros(max(off, 1), dtype=dtype, device=dev)
+        g = torch.zeros(max(off, 1), dtype=dtype, device=dev)
+        views = getattr(self, "_views", [])
+        for storage, members, o in plan:
+            n = storage.numel()
+            base_ptr = storage.data_ptr()
+            rel = [((m.data_ptr() - base_ptr) // storage.element_size(), m.shape) for m in members]
+            new = w[o:o + n].view(storage.shape)
+            new.copy_(storage.detach())
+            gview = g[o:o + n].view(storage.shape)
+            is_param = any(m is storage for m in members)
+            if is_param:
+                storage.data = new
+                storage.grad = gview
+            else:
+                storage.data = new                                   # plain fused tensor re-pointed in place (id preserved)
+                for m, (r, shp) in zip(members, rel):
+                    k = m.numel()
+                    m.data = w[o + r:o + r + k].view(shp)
+                    m.grad = g[o + r:o + r + k].view(shp)
+            views.append((storage, gview))
+        self._views = views
+        setattr(self, "w" + tag, w)
+        setattr(self, "g" + tag, g)
+        return off
+
+    # ---------------------------------------------------------------------------------------------
+    def zero_grad(self):
+        if self.n16:
+            self.g16.zero_()
+        if self.n32:
+            self.g32.zero_()
+
+    def allreduce_grads(self):
+        """The one exchange step of data parallelism: sum the flat student gradient buffers over NVLink (NCCL)."""
+        if self.world > 1:
+            if self.n16:
+                dist.all_reduce(self.g16, group=self.pg)
+            if self.n32:
+                dist.all_reduce(self.g32, group=self.pg)
+
+    def step(self, lr=None, grad_scale=1.0):
+        """AdamW step on the accumulated gradients.  ``grad_scale`` folds 1/(accumulation * world) into the update
+        (HF Trainer divides the loss instead; same arithmetic up to bf16 rounding of the scaled loss)."""
+        lr = self.lr if lr is None else lr
+        self.step_count += 1
+        self.allreduce_grads()
+        use_clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        if use_clip:
+            self.gnorm_sq.zero_()
+            if self.n16:
+                K.sumsq_(self.g16, self.gnorm_sq)
+            if self.n32:
+                K.sumsq_(self.g32, self.gnorm_sq)
+        gn = self.gnorm_sq if use_clip else None
+        mx = float(self.max_grad_norm) if use_clip else 0.0
+        if self.n16:
+            K.adamw_(self.master, self.m16, self.v16, self.g16, self.w16, lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                     self.step_count, gn, mx, grad_scale)
+        if self.n32:
+            K.adamw_(self.w32, self.m32, self.v32, self.g32, None, lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                     self.step_count, gn, mx, grad_scale)
+
+    def grad_norm(self, grad_scale=1.0):
+        return float(torch.sqrt(self.gnorm_sq)[0]) * grad_scale
+
+
+def cosine_lr(step, total, base_lr, warmup_ratio=0.03):
+    """transformers.get_cosine_schedule_with_warmup with warmup = ceil(ratio*total) (HF TrainingArguments.get_warmup_steps);
+    ``step`` = number of completed optimizer steps."""
+    warm = math.ceil(warmup_ratio * total)
+    if step < warm:
+        return base_lr * step / max(1, warm)
+    prog = (step - warm) / max(1, total - warm)
+    return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))

@@ -1,0 +1,190 @@
+"""Minimal trainer loop with the HF ``Trainer`` surface the reference's trainers rely on
+(``compute_loss`` / ``training_step`` / ``create_optimizer`` / ``log`` / ``save_model`` / ``_save_checkpoint``).
+
+The reference subclasses ``transformers.Trainer`` and runs under accelerate + DeepSpeed ZeRO-2
+(llavamod/train/align_trainer.py:180-309).  Here one process drives one GPU; gradient accumulation is local, the
+optimizer is the fused AdamW of ``engine.TrainState`` and the only collective is the student-gradient all-reduce.
+"""
+import glob
+import json
+import os
+import re
+import time
+from collections import defaultdict
+
+import torch
+import torch.distributed as dist
+
+from .engine import TrainState, cosine_lr
+
+
+class TrainerState:
+    def __init__(self):
+        self.global_step = 0
+        self.epoch = 0.0
+        self.log_history = []
+
+
+class BaseTrainer:
+    def __init__(self, model=None, args=None, data_collator=None, train_dataset=None, eval_dataset=None, tokenizer=None,
+                 model_init=None, compute_metrics=None, callbacks=None, optimizers=(None, None),
+                 preprocess_logits_for_metrics=None):
+        self.model = model
+        self.args = args
+        self.data_collator = data_collator
+        self.train_dataset = train_dataset
+        self.eval_dataset = eval_dataset
+        self.tokenizer = tokenizer
+        self.state = TrainerState()
+        self.optimizer = None
+        self.is_deepspeed_enabled = False
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world_size > 1 else 0
+        self._accum = 0
+        self._total_steps = None
+
+    # ---- optimizer ---------------------------------------------------------------------------------------
+    def create_optimizer(self):
+        """One AdamW group over every trainable parameter (reference: align_trainer.py:326-434 builds decay / no-decay /
+        projector-lr groups and MoE param groups; with --weight_decay 0. and no --mm_projector_lr, as in the distillation
+        shells, they collapse to this)."""
+        if self.optimizer is None:
+            a = self.args
+            if getattr(a, "mm_projector_lr", None) is not None:
+                raise NotImplementedError("--mm_projector_lr (separate projector LR group) is not used by the distillation shells")
+            self.optimizer = TrainState(self.model, lr=a.learning_rate, betas=(a.adam_beta1, a.adam_beta2), eps=a.adam_epsilon,
+                                        weight_decay=a.weight_decay, max_grad_norm=a.max_grad_norm)
+        return self.optimizer
+
+    def current_lr(self):
+        a = self.args
+        if self._total_steps is None or a.lr_scheduler_type == "constant":
+            return a.learning_rate
+        if a.lr_scheduler_type == "cosine":
+            return cosine_lr(self.state.global_step, self._total_steps, a.learning_rate, a.warmup_ratio)
+        if a.lr_scheduler_type == "linear":
+            import math
+            warm = math.ceil(a.warmup_ratio * self._total_steps)
+            s = self.state.global_step
+            if s < warm:
+                return a.learning_rate * s / max(1, warm)
+            return a.learning_rate * max(0.0, (self._total_steps - s) / max(1, self._total_steps - warm))
+        raise NotImplementedError("lr_scheduler_type %r" % a.lr_scheduler_type)
+
+    # ---- one micro-batch -----------------------------------------------------------------------------------
+    def compute_loss(self, model, inputs, return_outputs=False):
+        raise NotImplementedError
+
+    def training_step(self, model, inputs):
+        """forward + backward of one micro-batch; the optimizer step happens every ``gradient_accumulation_steps`` calls.
+        Gradients are accumulated UNSCALED; 1/(accum*world) is folded into the AdamW kernel."""
+        opt = self.create_optimizer()
+        model.train()
+        if self._accum == 0:
+            opt.zero_grad()
+        loss = self.compute_loss(model, inputs)
+        loss.backward()
+        self._accum += 1
+        if self._accum == self.args.gradient_accumulation_steps:
+            opt.step(lr=self.current_lr(), grad_scale=1.0 / (self._accum * self.world_size))
+            self._accum = 0
+            self.state.global_step += 1
+        return loss.detach()
+
+    # ---- loop ------------------------------------------------------------------------------------------------
+    def get_train_dataloader(self):
+        from torch.utils.data import DataLoader, DistributedSampler
+        sampler = DistributedSampler(self.train_dataset, shuffle=True, seed=self.args.seed) if self.world_size > 1 else None
+        return DataLoader(self.train_dataset, batch_size=self.args.per_device_train_batch_size, sampler=sampler,
+                          shuffle=(sampler is None), collate_fn=self.data_collator,
+                          num_workers=self.args.dataloader_num_workers, pin_memory=True, drop_last=True)
+
+    def train(self, resume_from_checkpoint=None):
+        a = self.args
+        dl = self.get_train_dataloader()
+        steps_per_epoch = max(1, len(dl) // a.gradient_accumulation_steps)
+        self._total_steps = a.max_steps if a.max_steps > 0 else int(steps_per_epoch * a.num_train_epochs)
+        if resume_from_checkpoint:
+            self._load_checkpoint(resume_from_checkpoint)
+        t0 = time.time()
+        tr_loss, n_loss = 0.0, 0
+        done = False
+        epoch = 0
+        while not done:
+            if hasattr(dl.sampler, "set_epoch"):
+                dl.sampler.set_epoch(epoch)
+            for batch in dl:
+                before = self.state.global_step
+                loss = self.training_step(self.model, batch)
+                tr_loss += float(loss); n_loss += 1
+                if self.state.global_step != before:
+                    s = self.state.global_step
+                    if a.logging_steps and s % a.logging_steps == 0:
+                        self.log({"loss": tr_loss / max(1, n_loss), "learning_rate": self.current_lr(), "epoch": s / steps_per_epoch})
+                        tr_loss, n_loss = 0.0, 0
+                    if a.save_strategy == "steps" and a.save_steps and s % a.save_steps == 0:
+                        self._save_checkpoint(self.model, None)
+                    if s >= self._total_steps:
+                        done = True
+                        break
+            epoch += 1
+        return {"train_runtime": time.time() - t0, "global_step": self.state.global_step}
+
+    # ---- logging / saving --------------------------------------------------------------------------------------
+    def log(self, logs):
+        logs = dict(logs)
+        logs["step"] = self.state.global_step
+        self.state.log_history.append(logs)
+        if self.rank == 0:
+            os.makedirs(self.args.output_dir, exist_ok=True)
+            with open(os.path.join(self.args.output_dir, "trainer_log.jsonl"), "a") as f:
+                f.write(json.dumps(logs) + "\n")
+            print(logs, flush=True)
+
+    def _get_output_dir(self, trial=None):
+        return self.args.output_dir
+
+    def save_model(self, output_dir=None):
+        self._save(output_dir or self.args.output_dir)
+
+    def _save(self, output_dir=None, state_dict=None):
+        if self.rank == 0:
+            self.model.save_pretrained(output_dir or self.args.output_dir, state_dict=state_dict)
+
+    def _save_checkpoint(self, model, trial, metrics=None):
+        """checkpoint-N/: HF-layout model + optimizer arenas + trainer state (reference: HF Trainer + DeepSpeed engine
+        checkpoints under each checkpoint-N/, align_train.py:601-604 auto-resume)."""
+        d = os.path.join(self._get_output_dir(trial), f"checkpoint-{self.state.global_step}")
+        if self.rank == 0:
+            self.model.save_pretrained(d)
+            opt = self.optimizer
+            if opt is not None:
+                torch.save({"master": opt.master, "m16": opt.m16, "v16": opt.v16, "w32": getattr(opt, "w32", None), "m32": opt.m32,
+                            "v32": opt.v32, "step_count": opt.step_count}, os.path.join(d, "optimizer.pt"))
+            with open(os.path.join(d, "trainer_state.json"), "w") as f:
+                json.dump({"global_step": self.state.global_step, "log_history": self.state.log_history}, f)
+            lim = self.args.save_total_limit
+            if lim:
+                cks = sorted(glob.glob(os.path.join(self._get_output_dir(trial), "checkpoint-*")),
+                             key=lambda p: int(re.findall(r"checkpoint-(\d+)", p)[-1]))
+                import shutil
+                for old in cks[:-lim]:
+                    shutil.rmtree(old, ignore_errors=True)
+        if self.world_size > 1:
+            dist.barrier()
+
+    def _load_checkpoint(self, d):
+        from ..model.builder_io import load_into, load_state_dict_files
+        if d is True:
+            cks = sorted(glob.glob(os.path.join(self.args.output_dir, "checkpoint-*")),
+                         key=lambda p: int(re.findall(r"checkpoint-(\d+)", p)[-1]))
+            d = cks[-1]
+        opt = self.create_optimizer()
+        load_into(self.model, load_state_dict_files(d), strict=False)
+        st = torch.load(os.path.join(d, "optimizer.pt"), map_location=self.model.device, weights_only=True)
+        for k in ("master", "m16", "v16", "m32", "v32"):
+            if st.get(k) is not None and getattr(opt, k) is not None:
+                getattr(opt, k).copy_(st[k])
+        opt.step_count = st["step_count"]
+        with open(os.path.join(d, "trainer_state.json")) as f:
+            self.state.global_step = json.load(f)["global_step"]

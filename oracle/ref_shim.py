@@ -44,7 +44,14 @@ _loaded = {}
 
 
 def load():
-    """Returns a namespace with the reference classes of the dense path."""
+    """Returns a namespace with the reference classes of the dense path.
+
+    The reference uses absolute ``llavamod.*`` imports, so it has to live under that name in ``sys.modules`` -- the same
+    name as the B200 package.  The two therefore never share a process: tests reach the reference through
+    ``run_child`` (a subprocess running ``oracle/ref_child.py``); only ``tests/golden/make_golden.py`` and that child
+    call ``load()`` directly."""
+    if "llavamod" in sys.modules and not getattr(sys.modules["llavamod"], "__path__", [""])[0].startswith(REF_ROOT):
+        raise RuntimeError("the B200 llavamod package is already imported in this process; use ref_shim.run_child()")
     if _loaded:
         return types.SimpleNamespace(**_loaded)
     if not available():
@@ -62,11 +69,20 @@ def load():
             import timm  # noqa: F401
         except Exception:
             import torch.nn as nn
-            t = types.ModuleType("timm"); t.__path__ = []
-            tm = types.ModuleType("timm.models"); tm.__path__ = []
-            tv = types.ModuleType("timm.models.vision_transformer")
-            tl = types.ModuleType("timm.models.layers")
-            tml = types.ModuleType("timm.layers")
+            import importlib.machinery as _mach
+
+            def _stub(name, pkg=False):
+                mod = types.ModuleType(name)
+                mod.__spec__ = _mach.ModuleSpec(name, None, is_package=pkg)   # transformers probes find_spec("timm")
+                if pkg:
+                    mod.__path__ = []
+                return mod
+
+            t = _stub("timm", True)
+            tm = _stub("timm.models", True)
+            tv = _stub("timm.models.vision_transformer")
+            tl = _stub("timm.models.layers")
+            tml = _stub("timm.layers")
 
             class Block(nn.Module):  # never instantiated on the dense path
                 pass
@@ -78,7 +94,7 @@ def load():
                 mod.trunc_normal_ = nn.init.trunc_normal_
                 mod.DropPath = nn.Identity
                 mod.Mlp = nn.Identity
-            tr = types.ModuleType("timm.models.regnet")
+            tr = _stub("timm.models.regnet")
             tr.RegStage = Block
             sys.modules.update({"timm": t, "timm.models": tm, "timm.models.vision_transformer": tv,
                                 "timm.models.layers": tl, "timm.layers": tml, "timm.models.regnet": tr})
@@ -134,3 +150,22 @@ def build_tiny_dense(tmpdir, hidden=128, inter=256, layers=2, heads=4, kv_heads=
     model.get_model().initialize_vision_modules(margs)
     model.eval()
     return model
+
+
+def run_child(request: dict, timeout=600):
+    """Runs oracle/ref_child.py in a clean subprocess (reference namespace isolated from the B200 package).
+    ``request`` = dict(kw=<build_tiny_dense kwargs>, input_ids, labels, attention_mask, images, padding_side).
+    Returns dict(state_dict, logits, labels, loss)."""
+    import subprocess
+    import tempfile
+    import torch
+    d = tempfile.mkdtemp()
+    req, resp = os.path.join(d, "req.pt"), os.path.join(d, "resp.pt")
+    torch.save(request, req)
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_child.py"), req, resp],
+                       capture_output=True, text=True, timeout=timeout, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("reference child failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+    return torch.load(resp, weights_only=False)

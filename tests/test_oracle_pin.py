@@ -6,7 +6,6 @@
 * live leg (only where /root/reference exists): fresh seeds / shapes through oracle/ref_shim.py.
 """
 import os
-import tempfile
 
 import pytest
 import torch
@@ -49,9 +48,7 @@ def test_restated_matches_reference_golden(name, golden_dir):
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not on this box")
 @pytest.mark.parametrize("seed,heads,kv,side", [(11, 4, 4, "right"), (12, 4, 1, "right"), (13, 2, 2, "left")])
 def test_restated_matches_reference_live(seed, heads, kv, side):
-    tmp = tempfile.mkdtemp()
-    m = ref_shim.build_tiny_dense(tmp, hidden=64, inter=96, layers=1, heads=heads, kv_heads=kv, vocab=97, seed=seed)
-    m.config.tokenizer_padding_side = side
+    """Fresh seeds / GQA / left padding through the reference itself (run in a child process, see ref_shim.load)."""
     g = torch.Generator().manual_seed(seed)
     B, T = 3, 12
     ids = torch.randint(0, 97, (B, T), generator=g)
@@ -59,26 +56,16 @@ def test_restated_matches_reference_live(seed, heads, kv, side):
     mask = torch.ones(B, T, dtype=torch.bool); mask[1, 8:] = False
     labels = ids.clone(); labels[:, :3] = -100
     images = [torch.randn(3, 32, 32, generator=g) for _ in range(4)]
-    ref = m(input_ids=ids, labels=labels, attention_mask=mask, images=images, return_dict=True)
+    kw = dict(hidden=64, inter=96, layers=1, heads=heads, kv_heads=kv, vocab=97, seed=seed)
+    ref = ref_shim.run_child(dict(kw=kw, input_ids=ids, labels=labels, attention_mask=mask, images=images, padding_side=side,
+                                  clip_images=torch.stack(images[:2])))
     cc = R.ClipCfg(hidden=64, inter=128, layers=3, heads=4, image=32, patch=8)
     lc = R.LMCfg(hidden=64, inter=96, layers=1, heads=heads, kv_heads=kv, vocab=97, kd_vocab=97)
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    sd = ref["state_dict"]
     out = R.llava_forward(sd, lc, cc, ids, mask, labels, images, padding_side=side)
-    assert torch.equal(out["labels"], ref.labels)
+    assert torch.equal(out["labels"], ref["labels"])
     valid = out["attention_mask"]
-    torch.testing.assert_close(out["logits"][valid], ref.logits[valid], rtol=2e-4, atol=2e-5)
-    torch.testing.assert_close(out["loss"], ref.loss.detach(), rtol=1e-5, atol=1e-6)
-
-
-@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not on this box")
-def test_clip_restatement_matches_hf_clip():
-    """The CLIP arithmetic is third-party (transformers.CLIPVisionModel, call site
-    multimodal_encoder/clip_encoder.py:30,54): check the plain-torch restatement against it."""
-    tmp = tempfile.mkdtemp()
-    m = ref_shim.build_tiny_dense(tmp, hidden=64, inter=96, layers=1, heads=2, kv_heads=2, vocab=97, seed=5)
-    tower = m.get_model().get_image_tower()
-    imgs = torch.randn(2, 3, 32, 32)
-    ref = tower(imgs)
-    cc = R.ClipCfg(hidden=64, inter=128, layers=3, heads=4, image=32, patch=8)
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
-    torch.testing.assert_close(R.clip_tower(sd, cc, imgs), ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out["logits"][valid], ref["logits"][valid], rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(out["loss"], ref["loss"], rtol=1e-5, atol=1e-6)
+    # CLIP arithmetic is third-party (transformers.CLIPVisionModel, call site clip_encoder.py:30,54)
+    torch.testing.assert_close(R.clip_tower(sd, cc, torch.stack(images[:2])), ref["clip_features"], rtol=1e-4, atol=1e-5)
