@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- LLaVA-MoD mimic-distillation step on B200 (BASELINE.json: distill samples/s; KL-kernel HBM GB/s vs peak;
+next to the reference CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            # our path (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own algorithm on the host cores (oracle)
+
+A "step" = one optimizer step of the reference recipe on every GPU: 8 micro-batches of one sample each
+(per_device_train_batch_size 1 x gradient_accumulation_steps 8, dense2sparse_distillation.sh:70-72), each micro-batch =
+CLIP tower forward + frozen 7B teacher forward + 0.5B-4E sparse student forward/backward + fused mimic-KL/LM loss,
+then gradient all-reduce (N > 1), global-norm clip and fused AdamW.  Synthetic inputs of the named shape
+(SURVEY.md section 8d): 336x336 image, 1473 text ids with one <image> -> spliced length 2048, first 40% masked.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "llava-mod_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (student arch, teacher arch, clip, spliced seq len, accumulation)
+    "mimic-0.5B-4E-from-7B-seq2048": dict(student="qwen1.5-0.5b", teacher="qwen1.5-7b", clip="clip-l-336", seq=2048, accum=8, experts=4),
+    "mimic-1.8B-8E-from-7B-seq4096": dict(student="qwen1.5-1.8b", teacher="qwen1.5-7b", clip="clip-l-336", seq=4096, accum=8, experts=8),
+    "tiny": dict(student="tiny", teacher="tiny", clip="tiny", seq=64, accum=2, experts=4),
+}
+FLOP_PER_SAMPLE = {"mimic-0.5B-4E-from-7B-seq2048": 38.5e12, "mimic-1.8B-8E-from-7B-seq4096": 115.7e12}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+def synth_batch(wl, rank, idx, vocab, device=None, pinned=False):
+    """One sample: ids with position 5 = -200, 40% instruction mask, all-true attention mask."""
+    from llavamod.model import synthetic as S
+    clip = S.CLIP[wl["clip"]]
+    P = (clip["image_size"] // clip["patch_size"]) ** 2
+    Tt = wl["seq"] - P + 1
+    g = torch.Generator().manual_seed(1234 + 1000 * rank + idx)
+    ids = torch.randint(0, vocab, (1, Tt), generator=g)
+    ids[0, 5] = -200
+    labels = ids.clone()
+    labels[0, : int(0.4 * Tt)] = -100
+    mask = torch.ones(1, Tt, dtype=torch.bool)
+    img = torch.randn(3, clip["image_size"], clip["image_size"], generator=g).to(torch.bfloat16)
+    if pinned:
+        ids, labels, mask, img = ids.pin_memory(), labels.pin_memory(), mask.pin_memory(), img.pin_memory()
+    return dict(input_ids=ids, labels=labels, attention_mask=mask, images=[img])
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the oracle (CPU restatement of the reference's algorithm) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def _cpu_setup(wl_name):
+    """Random weights / inputs of the bounded CPU sample, built once (weight generation is not part of the step)."""
+    from oracle import restated as R
+    from llavamod.model import synthetic as S
+    if wl_name in _CPU_CACHE:
+        return _CPU_CACHE[wl_name]
+    wl = WORKLOADS[wl_name]
+    g = torch.Generator().manual_seed(0)
+    sa, ta, ca = S.ARCH[wl["student"]], S.ARCH[wl["teacher"]], S.CLIP[wl["clip"]]
+    T = wl["seq"]
+    rows = min(256, T)
+    V = sa["vocab_size"]
+
+    def lm(arch, moe_layers=(), E=4):
+        return R.LMCfg(hidden=arch["hidden_size"], inter=arch["intermediate_size"], layers=1, heads=arch["num_attention_heads"],
+                       kv_heads=arch["num_key_value_heads"], vocab=64, rope_theta=arch["rope_theta"], moe_layers=list(moe_layers),
+                       num_experts=E, capacity_factor=1.5, kd_vocab=64)
+
+    c = dict(T=T, rows=rows, V=V, wl=wl, sa=sa, ta=ta, ca=ca)
+    c["tc"] = lm(ta)
+    c["t_sd"] = R.init_lm(c["tc"], 8, g)
+    c["t_x"] = torch.randn(1, T, ta["hidden_size"], generator=g)
+    c["students"] = []
+    for name, moe in (("student_dense_layer", ()), ("student_moe_layer", (0,))):
+        sc = lm(sa, moe, wl["experts"])
+        sd = R.init_lm(sc, 8, g)
+        for k in R.trainable_keys(sd):
+            sd[k].requires_grad_(True)
+        noise = [R.gumbel_noise((T, wl["experts"]), g)] if moe else None
+        c["students"].append((name, sc, sd, torch.randn(1, T, sa["hidden_size"], generator=g), noise))
+    c["cc"] = R.ClipCfg(hidden=ca["hidden_size"], inter=ca["intermediate_size"], layers=2, heads=ca["num_attention_heads"],
+                        image=ca["image_size"], patch=ca["patch_size"], select_layer=-2)
+    c["c_sd"] = R.init_clip(c["cc"], g)
+    c["img"] = torch.randn(1, 3, ca["image_size"], ca["image_size"], generator=g)
+    c["wt"] = torch.empty(V, ta["hidden_size"]).normal_(0, 0.02, generator=g)
+    c["ws"] = torch.empty(V, sa["hidden_size"]).normal_(0, 0.02, generator=g)
+    c["ht"] = torch.randn(1, rows, ta["hidden_size"], generator=g)
+    c["hs"] = torch.randn(1, rows, sa["hidden_size"], generator=g)
+    c["labels"] = torch.randint(0, V, (1, rows), generator=g)
+    _CPU_CACHE[wl_name] = c
+    return c
+
+
+def cpu_step_sample(wl_name, threads):
+    """One bounded CPU sample of the step: one layer of each kind at the full shapes (T'), the two lm_heads + mimic/LM loss
+    on 256 of the T' rows, extrapolated by layer counts / row ratio to seconds per SAMPLE.
+    Returns (seconds per sample, description, parts)."""
+    from oracle import restated as R
+    torch.set_num_threads(threads)
+    c = _cpu_setup(wl_name)
+    T, rows, V, sa, ta, ca = c["T"], c["rows"], c["V"], c["sa"], c["ta"], c["ca"]
+    t = {}
+    with torch.no_grad():                                                   # teacher: one dense layer forward
+        t0 = time.perf_counter(); R.lm_forward(c["t_sd"], c["tc"], c["t_x"], None, None); t["teacher_layer_fwd"] = time.perf_counter() - t0
+    for name, sc, sd, x0, noise in c["students"]:                           # student layers: forward + backward
+        for k in sd:
+            sd[k].grad = None
+        x = x0.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        h, la = R.lm_forward(sd, sc, x, None, None, noise)
+        (h.sum() + (sum(la) if la else 0.0)).backward()
+        t[name + "_fwd_bwd"] = time.perf_counter() - t0
+    with torch.no_grad():
+        t0 = time.perf_counter(); R.clip_tower(c["c_sd"], c["cc"], c["img"]); t["clip_layer_fwd"] = time.perf_counter() - t0
+    hs = c["hs"].clone().requires_grad_(True)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        tl = torch.nn.functional.linear(c["ht"], c["wt"]).float()
+    sl = torch.nn.functional.linear(hs, c["ws"]).float()
+    out = dict(logits=sl, labels=c["labels"], loss=R.shifted_ce(sl, c["labels"], V), moe_loss=None)
+    loss, _ = R.mimic_compute_loss(out, tl, "kd_lm", False, False, V)
+    loss.backward()
+    t["heads_and_losses_%drows" % rows] = time.perf_counter() - t0
+    n_moe = len(range(sa["num_hidden_layers"])[::2])
+    per_sample = (ta["num_hidden_layers"] * t["teacher_layer_fwd"] + (sa["num_hidden_layers"] - n_moe) * t["student_dense_layer_fwd_bwd"]
+                  + n_moe * t["student_moe_layer_fwd_bwd"] + 2 * (ca["num_hidden_layers"] - 1) * t["clip_layer_fwd"]
+                  + (T / rows) * t["heads_and_losses_%drows" % rows])
+    desc = ("oracle (CPU restatement of the reference, fp32, %d threads): 1 teacher layer fwd + 1 dense and 1 MoE student layer fwd/bwd + "
+            "1 CLIP layer at the full T'=%d shapes, lm_heads + mimic/LM loss on %d of %d rows; extrapolated by layer counts "
+            "(%d teacher / %d dense + %d MoE student / 2x%d CLIP) and rows to one sample"
+            % (threads, T, rows, T, ta["num_hidden_layers"], sa["num_hidden_layers"] - n_moe, n_moe, ca["num_hidden_layers"] - 1))
+    return per_sample, desc, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    wl_name = args.workload
+    _cpu_setup(wl_name)
+    for _ in range(args.warmup):
+        cpu_step_sample(wl_name, threads)
+    t0 = time.perf_counter()
+    per = []
+    for _ in range(args.steps):
+        s, desc, _ = cpu_step_sample(wl_name, threads)
+        per.append(s)
+    wall = time.perf_counter() - t0
+    sec_per_sample = sum(per) / len(per)
+    value = 1.0 / sec_per_sample
+    accum = WORKLOADS[wl_name]["accum"]
+    line = {"impl": "reference", "metric": "distill_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_sample * accum, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": wl_name, "seq_len": WORKLOADS[wl_name]["seq"], "micro_batch": 1,
+                                                             "grad_accum": accum, "note": "ms_per_step extrapolated from the bounded sample"},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from llavamod import _C, kernels as K
+    from llavamod.model import synthetic as S
+    from tests.helpers import make_trainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    wl_name = args.workload
+    wl = WORKLOADS[wl_name]
+    accum = wl["accum"]
+    teacher = S.make_teacher(wl["teacher"], wl["clip"], device=dev, seed=0)
+    student = S.make_student(wl["student"], wl["clip"], device=dev, seed=1, margs=S.moe_args(num_experts=wl["experts"]), share_tower_with=teacher)
+    trainer = make_trainer(student, teacher, loss_type="kd_lm", accum=accum, lr=2e-5, max_steps=1000)
+    trainer.world_size = world
+    opt = trainer.create_optimizer()
+    V = student.config.vocab_size
+    nb = accum * 2
+    host_batches = [synth_batch(wl, rank, i, V, pinned=True) for i in range(nb)]
+    # device-resident copies (images + precomputed splice plan) for the `value` measurement
+    res_batches = []
+    for b in host_batches:
+        plan = student.make_splice_plan(b["input_ids"], b["attention_mask"], b["labels"])
+        res_batches.append(dict(input_ids=b["input_ids"], labels=b["labels"], attention_mask=b["attention_mask"],
+                                images=torch.stack(b["images"]).to(dev), splice_plan=plan))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(batches, n_steps, read_loss):
+        it = 0
+        last = None
+        for _ in range(n_steps):
+            for _ in range(accum):
+                last = trainer.training_step(student, batches[it % nb])
+                it += 1
+            if read_loss:
+                _ = float(last)           # D2H read of the step's loss
+        return last
+
+    # ---- value: device-resident inputs ----
+    run(res_batches, args.warmup, False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    K.TIMERS = {}
+    _C.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = run(res_batches, args.steps, False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _C.launch_count()
+    timers, K.TIMERS = K.TIMERS, None
+    clocks = sampler.finish()
+    final_loss = float(last)
+    # ---- e2e: host (pinned) buffers through the public trainer call, H2D copies + loss read inside the timed region ----
+    run(host_batches, 1, True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    run(host_batches, args.steps, True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    samples = args.steps * accum * world
+    value = samples / (ms / 1e3)
+    e2e = samples / (ms_e2e / 1e3)
+    hbm_peak, tf_peak, src = peaks()
+    # KL roofline: algorithmic bytes / CUDA-event duration of the kernel itself
+    T = wl["seq"]
+    lab = res_batches[0]["splice_plan"]["labels"].cpu()
+    m_kd = lab != -100
+    m_ce = torch.cat([lab[:, 1:] != -100, torch.zeros(lab.shape[0], 1, dtype=torch.bool)], 1)
+    active = int((m_kd | m_ce).sum())
+    kd_vocab = min(151936, V)
+    bytes_launch = active * 6 * kd_vocab + (T - active) * 2 * kd_vocab
+    ev = timers.get("kl_fwd_bwd", [])
+    kl_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+    ach = bytes_launch / (kl_ms * 1e-3) / 1e9 if kl_ms > 0 else None
+    prof = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "kl_traffic.json")) as f:
+            prof = json.load(f)
+    except Exception:
+        pass
+    img_bytes = host_batches[0]["images"][0].numel() * 2
+    plan_bytes = 5 * T * 8
+    line = {
+        "metric": "distill_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl_name, "student": wl["student"] + "-%dE-top2" % wl["experts"], "teacher": wl["teacher"], "vision": wl["clip"],
+                   "seq_len": T, "micro_batch": 1, "grad_accum": accum, "global_batch": accum * world, "loss": "kd_lm (mimic KL + LM + aux)",
+                   "parallelism": "dp%d" % world, "l2": "working set per micro-batch (15.4 GB of teacher weights) >> 126 MB L2; no explicit flush",
+                   "gemm": "cuBLAS (library) for plain GEMMs, flash-attn (library) attention; all other ops are liblmod_b200 kernels"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": accum * (img_bytes + plan_bytes), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "roofline": {"kernel": "kl_fused_kernel (lmod_kl_fwd_bwd)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (ach / hbm_peak) if ach else None, "peak_source": src, "traffic": prof.get("traffic_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": kl_ms, "launches_timed": len(ev),
+                     "note": "%d of %d rows active (6V B each), masked rows zero-filled (2V B); survey-style 6V*N would read %.1f GB/s"
+                             % (active, T, (T * 6 * kd_vocab) / (kl_ms * 1e-3) / 1e9 if kl_ms > 0 else 0.0)},
+        "step_tensor_util": ({"tflops_per_gpu": FLOP_PER_SAMPLE[wl_name] * value / world / 1e12, "peak_tflops": tf_peak,
+                              "frac": FLOP_PER_SAMPLE[wl_name] * value / world / 1e12 / tf_peak} if wl_name in FLOP_PER_SAMPLE else None),
+        "final_loss": final_loss,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        s, desc, parts = cpu_step_sample(wl_name, threads)
+        line["cpu_baseline"] = {"value": 1.0 / s, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc, "parts_s": parts}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mimic-0.5B-4E-from-7B-seq2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

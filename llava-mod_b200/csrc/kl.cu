@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t hmin2_u32(uint32_t a, uint32_t b) {
 
 template <bool CHECK_INF>
 __device__ __forceinline__ void accum_pair(uint32_t sw, uint32_t tw, float nms, float nmt, float& zs,
-                                           float& zt, float& a) {
+                                           float& zt, float& a, float& zk) {
   float s0 = bf16lo(sw), s1 = bf16hi(sw), t0 = bf16lo(tw), t1 = bf16hi(tw);
   float es0 = ex2f(fmaf(s0, LOG2E_F, nms)), es1 = ex2f(fmaf(s1, LOG2E_F, nms));
   float et0 = ex2f(fmaf(t0, LOG2E_F, nmt)), et1 = ex2f(fmaf(t1, LOG2E_F, nmt));
@@ -60,6 +60,7 @@ __device__ __forceinline__ void accum_pair(uint32_t sw, uint32_t tw, float nms, 
   if (CHECK_INF) {   // align_trainer.py:509-510: terms where log q_S is +-inf are dropped
     if (isinf(s0)) { s0 = 0.f; et0 = 0.f; }
     if (isinf(s1)) { s1 = 0.f; et1 = 0.f; }
+    zk += et0; zk += et1;      // teacher mass of the KEPT terms: x = sum_kept p_T*(s - lse_S)
   }
   a = fmaf(et0, s0, a);
   a = fmaf(et1, s1, a);
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(16) Xchg xchg[2];
   __shared__ __align__(8) uint64_t bars[KL_CHUNKS];
-  __shared__ float red[6][KL_THREADS / 32];
+  __shared__ float red[7][KL_THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank(), cs = cluster_nctarank();
@@ -167,35 +168,37 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
     const float ms_u = isinf(ms) ? 0.f : ms, mt_u = isinf(mt) ? 0.f : mt;   // guard (-inf) - (-inf)
 
     // ---- pass B: local sum-exp and sum e^{t-mt} * s ----
-    float zs = 0.f, zt = 0.f, acc = 0.f;
+    float zs = 0.f, zt = 0.f, acc = 0.f, zk = 0.f;
     {
       const float nms = -ms_u * LOG2E_F, nmt = -mt_u * LOG2E_F;
       if (!has_inf) {
         for (int i = tid; i < nvec; i += KL_THREADS) {
           uint4 sv = s_buf[i], tv = t_buf[i];
-          accum_pair<false>(sv.x, tv.x, nms, nmt, zs, zt, acc);
-          accum_pair<false>(sv.y, tv.y, nms, nmt, zs, zt, acc);
-          accum_pair<false>(sv.z, tv.z, nms, nmt, zs, zt, acc);
-          accum_pair<false>(sv.w, tv.w, nms, nmt, zs, zt, acc);
+          accum_pair<false>(sv.x, tv.x, nms, nmt, zs, zt, acc, zk);
+          accum_pair<false>(sv.y, tv.y, nms, nmt, zs, zt, acc, zk);
+          accum_pair<false>(sv.z, tv.z, nms, nmt, zs, zt, acc, zk);
+          accum_pair<false>(sv.w, tv.w, nms, nmt, zs, zt, acc, zk);
         }
       } else {
         for (int i = tid; i < nvec; i += KL_THREADS) {
           uint4 sv = s_buf[i], tv = t_buf[i];
-          accum_pair<true>(sv.x, tv.x, nms, nmt, zs, zt, acc);
-          accum_pair<true>(sv.y, tv.y, nms, nmt, zs, zt, acc);
-          accum_pair<true>(sv.z, tv.z, nms, nmt, zs, zt, acc);
-          accum_pair<true>(sv.w, tv.w, nms, nmt, zs, zt, acc);
+          accum_pair<true>(sv.x, tv.x, nms, nmt, zs, zt, acc, zk);
+          accum_pair<true>(sv.y, tv.y, nms, nmt, zs, zt, acc, zk);
+          accum_pair<true>(sv.z, tv.z, nms, nmt, zs, zt, acc, zk);
+          accum_pair<true>(sv.w, tv.w, nms, nmt, zs, zt, acc, zk);
         }
       }
     }
-    zs = warp_sum(zs); zt = warp_sum(zt); acc = warp_sum(acc);
-    if (lane == 0) { red[3][warp] = zs; red[4][warp] = zt; red[5][warp] = acc; }
+    if (!has_inf) zk = zt;
+    zs = warp_sum(zs); zt = warp_sum(zt); acc = warp_sum(acc); zk = warp_sum(zk);
+    if (lane == 0) { red[3][warp] = zs; red[4][warp] = zt; red[5][warp] = acc; red[6][warp] = zk; }
     __syncthreads();
     if (warp == 0) {
       float a = (lane < KL_THREADS / 32) ? red[3][lane] : 0.f;
       float b = (lane < KL_THREADS / 32) ? red[4][lane] : 0.f;
       float c = (lane < KL_THREADS / 32) ? red[5][lane] : 0.f;
-      a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+      float k = (lane < KL_THREADS / 32) ? red[6][lane] : 0.f;
+      a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); k = warp_sum(k);
       if (lane == 0) {
         float slab = 0.f;
         if (m_ce) {
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
         }
         Xchg x;
         x.ms = (nvec > 0) ? ms : -INFINITY; x.mt = (nvec > 0) ? mt : -INFINITY;
-        x.zs = a; x.zt = b; x.a = c; x.slab = slab; x.pad0 = 0.f; x.pad1 = 0.f;
+        x.zs = a; x.zt = b; x.a = c; x.slab = slab; x.pad0 = k; x.pad1 = 0.f;
         xchg[par] = x;
       }
     }
@@ -213,22 +216,22 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
     cluster_sync_all();
     float lse_s, lse_t, xrow, slab;
     {
-      float r_ms = -INFINITY, r_mt = -INFINITY, r_zs = 0.f, r_zt = 0.f, r_a = 0.f, r_sl = 0.f;
+      float r_ms = -INFINITY, r_mt = -INFINITY, r_zs = 0.f, r_zt = 0.f, r_a = 0.f, r_sl = 0.f, r_zk = 0.f;
       if ((uint32_t)lane < cs) {
         const float* base = reinterpret_cast<const float*>(&xchg[par]);
         r_ms = dsmem_ld_f32(base + 0, lane); r_mt = dsmem_ld_f32(base + 1, lane);
         r_zs = dsmem_ld_f32(base + 2, lane); r_zt = dsmem_ld_f32(base + 3, lane);
-        r_a = dsmem_ld_f32(base + 4, lane);  r_sl = dsmem_ld_f32(base + 5, lane);
+        r_a = dsmem_ld_f32(base + 4, lane);  r_sl = dsmem_ld_f32(base + 5, lane); r_zk = dsmem_ld_f32(base + 6, lane);
       }
       float Ms = warp_max(r_ms), Mt = warp_max(r_mt);
       float Ms_u = isinf(Ms) ? 0.f : Ms, Mt_u = isinf(Mt) ? 0.f : Mt;
       float fs = isinf(r_ms) ? 0.f : ex2f((r_ms - Ms_u) * LOG2E_F);
       float ft = isinf(r_mt) ? 0.f : ex2f((r_mt - Mt_u) * LOG2E_F);
-      float Zs = warp_sum(r_zs * fs), Zt = warp_sum(r_zt * ft), A = warp_sum(r_a * ft);
+      float Zs = warp_sum(r_zs * fs), Zt = warp_sum(r_zt * ft), A = warp_sum(r_a * ft), Zk = warp_sum(r_zk * ft);
       slab = warp_sum(r_sl);
       lse_s = Ms_u + lg2f(Zs) * LN2_F;
       lse_t = Mt_u + lg2f(Zt) * LN2_F;
-      xrow = A / Zt - lse_s;
+      xrow = (A - lse_s * Zk) / Zt;
     }
     if (rank == 0 && tid == 0) {
       float4 o = make_float4(xrow, m_ce ? (lse_s - slab) : 0.f, lse_s, lse_t);

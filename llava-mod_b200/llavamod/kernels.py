@@ -403,6 +403,26 @@ def moe_forward_nograd(x, res, wg, w_gu, w_dn, noise, cf, min_cap):
 # ---------------------------------------------------------------------------------------------------
 # fused lm_head + mimic-KL (+ shifted CE) loss head
 # ---------------------------------------------------------------------------------------------------
+# optional per-kernel device timing (bench.py roofline): name -> list of (start_event, end_event) on the launching stream
+TIMERS = None
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMERS is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            self.b.record()
+            TIMERS.setdefault(self.name, []).append((self.a, self.b))
+
+
 def kl_fused(s_logits, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all=False, dlogits=None):
     """Raw kernel call.  s_logits/t_logits [N,ld] bf16, labels [N] int64.  Returns (out4, row_out).
     out4 = {align_loss, ce_loss, n_kd, n_ce}.  dlogits (may alias s_logits) receives the gradient."""
@@ -414,9 +434,10 @@ def kl_fused(s_logits, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all
     out4 = torch.empty(4, dtype=torch.float32, device=dev)
     da = 1 if distill_all else 0
     call("lmod_kl_counts", ptr(labels), N, seq_len, da, ptr(counts))
-    call("lmod_kl_fwd_bwd", ptr(s_logits), s_logits.stride(0), ptr(t_logits), t_logits.stride(0), ptr(labels), N, seq_len, vocab, da,
-         float(w_kd), float(w_ce), ptr(counts), ptr(row_out), ptr(dlogits) if dlogits is not None else None,
-         dlogits.stride(0) if dlogits is not None else 0)
+    with _Timed("kl_fwd_bwd"):
+        call("lmod_kl_fwd_bwd", ptr(s_logits), s_logits.stride(0), ptr(t_logits), t_logits.stride(0), ptr(labels), N, seq_len, vocab, da,
+             float(w_kd), float(w_ce), ptr(counts), ptr(row_out), ptr(dlogits) if dlogits is not None else None,
+             dlogits.stride(0) if dlogits is not None else 0)
     call("lmod_kl_finalize", ptr(row_out), ptr(labels), N, seq_len, da, ptr(out4))
     return out4, row_out
 

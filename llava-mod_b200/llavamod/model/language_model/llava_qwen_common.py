@@ -109,11 +109,11 @@ class LlavaQwenForCausalLMBase(nn.Module, LlavaMetaForCausalLM):
 
     # ---- forward -------------------------------------------------------------------------------------
     def forward_hidden(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, labels=None,
-                       images=None, moe_noise=None, tower_features=None):
+                       images=None, moe_noise=None, tower_features=None, plan=None):
         """Splice + decoder.  Returns dict(hidden [B,T',H], labels [B,T'], attention_mask, l_aux list)."""
         if inputs_embeds is None:
             (_, position_ids, attention_mask, _, inputs_embeds, labels) = self.prepare_inputs_labels_for_multimodal(
-                input_ids, position_ids, attention_mask, None, labels, images, tower_features=tower_features)
+                input_ids, position_ids, attention_mask, None, labels, images, tower_features=tower_features, plan=plan)
             if inputs_embeds is None:                       # text-only batch
                 ids = input_ids.to(self.device)
                 inputs_embeds = torch.nn.functional.embedding(ids, self.model.embed_tokens.weight)
@@ -123,6 +123,8 @@ class LlavaQwenForCausalLMBase(nn.Module, LlavaMetaForCausalLM):
                     labels = labels.to(self.device)
         hidden, l_auxes, records = self.model(inputs_embeds, attention_mask, position_ids, moe_noise=moe_noise,
                                               training_moe=self.training)
+        if hasattr(attention_mask, "mask"):
+            attention_mask = attention_mask.mask
         return dict(hidden=hidden, labels=labels, attention_mask=attention_mask, l_aux=l_auxes, records=records)
 
     def moe_loss_from(self, l_auxes):

@@ -65,6 +65,16 @@ def splice_plan(input_ids, attention_mask, labels, n_patches, padding_side="righ
     return src, nl, nm, pos, img
 
 
+class _AllTrue:
+    """Wrapper telling the decoder the mask has no padding without a device sync (``bool(mask.all())`` would sync)."""
+
+    def __init__(self, mask):
+        self.mask = mask
+
+    def all(self):
+        return True
+
+
 class LlavaMetaModel:
     """Mixin for the ``model`` attribute (reference: llava_arch.py:27-128)."""
 
@@ -134,8 +144,25 @@ class LlavaMetaForCausalLM(ABC):
         out = self.get_model().mm_projector.forward_image(tower_features.reshape(n * P, C))
         return out.view(n, P, -1)
 
+    def make_splice_plan(self, input_ids, attention_mask, labels, n_patches=None, device=None):
+        """Host integer plan -> device tensors; reusable across the teacher and the student forward of one micro-batch."""
+        tower = self.get_image_tower()
+        n_patches = n_patches if n_patches is not None else tower.num_patches
+        dev = device if device is not None else self.get_model().embed_tokens.weight.device
+        ids_h = input_ids.cpu().numpy() if torch.is_tensor(input_ids) else input_ids
+        am_h = None if attention_mask is None else (attention_mask.cpu().numpy() if torch.is_tensor(attention_mask) else attention_mask)
+        lb_h = None if labels is None else (labels.cpu().numpy() if torch.is_tensor(labels) else labels)
+        side = getattr(self.config, "tokenizer_padding_side", "right")
+        src, nl, nm, pos, img = splice_plan(ids_h, am_h, lb_h, n_patches, side, getattr(self.config, "tokenizer_model_max_length", None))
+        host = torch.from_numpy(np.stack([src, nl, pos, img, nm.astype(np.int64)]))
+        if dev.type == "cuda":
+            host = host.pin_memory()
+        plan = host.to(dev, non_blocking=True)
+        return dict(src=plan[0].contiguous(), labels=plan[1], pos=plan[2], img=plan[3].contiguous(), mask=plan[4].bool(),
+                    all_true=bool(nm.all()), has_labels=labels is not None, has_mask=attention_mask is not None, n_patches=n_patches)
+
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images,
-                                             tower_features=None):
+                                             tower_features=None, plan=None):
         tower = self.get_image_tower()
         if tower is None or images is None or input_ids.shape[1] == 1:
             return input_ids, position_ids, attention_mask, past_key_values, None, labels
@@ -145,15 +172,11 @@ class LlavaMetaForCausalLM(ABC):
         imgs = torch.stack([im.to(dev, non_blocking=True) for im in images]) if not torch.is_tensor(images) else images.to(dev)
         feats = self.encode_images(imgs, tower_features)                                   # [n_img, P, H]
         n_patches = feats.shape[1]
-        # host-side integer plan (a device tensor costs one sync, exactly like the reference's .sum()/.tolist())
-        ids_h = input_ids.cpu().numpy() if torch.is_tensor(input_ids) else input_ids
-        am_h = None if attention_mask is None else (attention_mask.cpu().numpy() if torch.is_tensor(attention_mask) else attention_mask)
-        lb_h = None if labels is None else (labels.cpu().numpy() if torch.is_tensor(labels) else labels)
-        side = getattr(self.config, "tokenizer_padding_side", "right")
-        src, nl, nm, pos, img = splice_plan(ids_h, am_h, lb_h, n_patches, side, getattr(self.config, "tokenizer_model_max_length", None))
-        plan = torch.from_numpy(np.stack([src, nl, pos, img])).to(dev, non_blocking=True)
-        src_d, nl_d, pos_d, img_d = plan[0], plan[1], plan[2], plan[3]
-        embeds = K.splice_embed(feats, self.get_model().embed_tokens.weight, src_d.contiguous(), img_d.contiguous(), n_patches)
-        new_mask = None if attention_mask is None else torch.from_numpy(nm).to(dev, non_blocking=True)
-        self._last_mask_all_true = bool(nm.all())
-        return None, (None if position_ids is None and False else pos_d), new_mask, past_key_values, embeds, (None if labels is None else nl_d)
+        if plan is None:   # host-side integer plan (a device tensor costs one sync, exactly like the reference's .sum()/.tolist())
+            plan = self.make_splice_plan(input_ids, attention_mask, labels, n_patches, dev)
+        embeds = K.splice_embed(feats, self.get_model().embed_tokens.weight, plan["src"], plan["img"], n_patches)
+        if not plan["has_mask"]:
+            new_mask = None
+        else:       # _AllTrue: "no padding" is known on the host, the decoder must not sync to find out
+            new_mask = _AllTrue(plan["mask"]) if plan["all_true"] else plan["mask"]
+        return None, plan["pos"], new_mask, past_key_values, embeds, (plan["labels"] if plan["has_labels"] else None)

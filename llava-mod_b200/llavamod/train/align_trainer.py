@@ -122,10 +122,14 @@ class AlignTrainer(BaseTrainer):
                 imgs = torch.stack([im.to(dev, non_blocking=True) for im in images]) if not torch.is_tensor(images) else images.to(dev)
                 fwd["images"] = imgs
                 tower_feats = model.get_image_tower()(imgs.to(model.dtype))
-            t = ref.forward_hidden(**fwd, tower_features=tower_feats)
+            plan = inputs.get("splice_plan")
+            if plan is None and images is not None and model.get_image_tower() is not None and \
+                    model.get_image_tower().num_patches == ref.get_image_tower().num_patches:
+                plan = model.make_splice_plan(fwd["input_ids"], fwd["attention_mask"], fwd["labels"])     # one host plan for both models
+            t = ref.forward_hidden(**fwd, tower_features=tower_feats, plan=plan)
             th = t["hidden"]
             t_logits = K.mm_nt(th.reshape(-1, th.shape[-1]), ref.lm_head.weight)              # teacher logits, bf16 [N, Vt]
-        s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"))
+        s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"), plan=plan)
         labels = s["labels"]
         if s["hidden"].shape[:2] != labels.shape or th.shape[:2] != labels.shape:
             raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")

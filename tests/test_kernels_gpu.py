@@ -129,7 +129,9 @@ def test_logp_gather_matches_oracle(B, T, V):
     seq, tok, lse = K.logp_gather(ld, labels.to(dev()))
     torch.testing.assert_close(seq.cpu(), ref.detach(), rtol=2e-5, atol=2e-4)
     d = torch.empty(B, T, Vp, dtype=torch.bfloat16, device=dev())[..., :V]
-    K.call("lmod_logp_gather_bwd", K.ptr(ld), ld.stride(1), K.ptr(labels.to(dev())), B, T, V, K.ptr(lse), K.ptr(gs.to(dev())), 0, K.ptr(d), d.stride(1))
+    lab_d, gs_d = labels.to(dev()), gs.to(dev())          # keep the device buffers alive across the raw-pointer call
+    K.call("lmod_logp_gather_bwd", K.ptr(ld), ld.stride(1), K.ptr(lab_d), B, T, V, K.ptr(lse), K.ptr(gs_d), 0, K.ptr(d), d.stride(1))
+    torch.cuda.synchronize()
     bf16_close(d, lf.grad.to(torch.bfloat16), atol=2e-7, msg="dlogits(logp)")
 
 
@@ -283,7 +285,8 @@ def test_rope_matches_reference_rounding():
     # backward = transpose rotation: <rope(x), y> == <x, rope_bwd(y)>
     y = torch.randn_like(qkv.float()).to(torch.bfloat16)
     yb = y.to(dev()).clone()
-    K.call("lmod_rope", K.ptr(yb), yb.shape[1], nh, yb.data_ptr() + nh * hd * 2, yb.shape[1], nkv, hd, K.ptr(cd), K.ptr(sn), K.ptr(pos.to(dev())), B * T, 1)
+    pos_d = pos.to(dev())
+    K.call("lmod_rope", K.ptr(yb), yb.shape[1], nh, yb.data_ptr() + nh * hd * 2, yb.shape[1], nkv, hd, K.ptr(cd), K.ptr(sn), K.ptr(pos_d), B * T, 1)
     lhs = (out[:, :(nh + nkv) * hd].float() * y[:, :(nh + nkv) * hd].float()).sum()
     rhs = (qkv[:, :(nh + nkv) * hd].float() * yb.cpu()[:, :(nh + nkv) * hd].float()).sum()
     assert abs(lhs - rhs) < 2e-2 * abs(lhs) + 0.5
