@@ -168,6 +168,41 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ q, int64_t ld_q, int nh,
   base[i + half] = __float2bfloat16_rn(o2);
 }
 
+// vectorised form (hd % 16 == 0): one thread rotates 8 (x1, x2) pairs with 16-byte accesses
+__global__ void __launch_bounds__(256) rope_vec_kernel(__nv_bfloat16* __restrict__ q, int64_t ld_q, int nh, __nv_bfloat16* __restrict__ k,
+                                                      int64_t ld_k, int nkv, int hd, const __nv_bfloat16* __restrict__ cos_t,
+                                                      const __nv_bfloat16* __restrict__ sin_t, const int64_t* __restrict__ pos, int64_t rows,
+                                                      int backward) {
+  const int half = hd >> 1, vph = half >> 3;
+  const int per_row = (nh + nkv) * vph;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * per_row) return;
+  const int64_t row = gid / per_row;
+  const int r = (int)(gid % per_row);
+  const int head = r / vph, v = r % vph;
+  __nv_bfloat16* base = (head < nh) ? (q + row * ld_q + (size_t)head * hd) : (k + row * ld_k + (size_t)(head - nh) * hd);
+  const int64_t pp = pos[row];
+  float c[8], s[8], x1[8], x2[8], o1[8], o2[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(cos_t + pp * hd) + v), c);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(sin_t + pp * hd) + v), s);
+  uint4* p1 = reinterpret_cast<uint4*>(base) + v;
+  uint4* p2 = reinterpret_cast<uint4*>(base + half) + v;
+  unpack8(*p1, x1);
+  unpack8(*p2, x2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (!backward) {
+      o1[j] = bf16_round(x1[j] * c[j]) + bf16_round(-x2[j] * s[j]);
+      o2[j] = bf16_round(x2[j] * c[j]) + bf16_round(x1[j] * s[j]);
+    } else {
+      o1[j] = x1[j] * c[j] + x2[j] * s[j];
+      o2[j] = x2[j] * c[j] - x1[j] * s[j];
+    }
+  }
+  *p1 = pack8(o1);
+  *p2 = pack8(o2);
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // out = bf16( bf16(silu(g)) * u ),  gate_up = [rows, 2I] (gate | up)
@@ -311,6 +346,14 @@ extern "C" int lmod_layernorm_fwd(const void* x, const void* w, const void* b, i
 extern "C" int lmod_rope(void* q, int64_t ld_q, int nh, void* k, int64_t ld_k, int nkv, int hd, const void* cos_table,
                          const void* sin_table, const int64_t* position_ids, int64_t rows, int backward, void* stream) {
   LMOD_CHECK_ARG(q && k && cos_table && sin_table && position_ids && rows > 0 && hd % 2 == 0, "lmod_rope: bad arguments");
+  if (hd % 16 == 0 && ld_q % 8 == 0 && ld_k % 8 == 0 && ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0)) {
+    const int64_t nv = rows * (nh + nkv) * (hd / 16);
+    rope_vec_kernel<<<GRID1D(nv, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)q, ld_q, nh, (__nv_bfloat16*)k, ld_k, nkv, hd,
+                                                                     (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table,
+                                                                     position_ids, rows, backward);
+    LMOD_LAUNCH_OK();
+    return LMOD_OK;
+  }
   const int64_t n = rows * (nh + nkv) * (hd / 2);
   rope_kernel<<<GRID1D(n, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)q, ld_q, nh, (__nv_bfloat16*)k, ld_k, nkv, hd,
                                                                (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table,
