@@ -153,25 +153,27 @@ int lmod_adamw(float* master, float* m, float* v, const void* grad, int grad_is_
                int64_t count, float lr, float beta1, float beta2, float eps, float wd, int64_t step,
                const float* gnorm_sq /* optional */, float max_norm, float grad_scale, void* stream);
 
-/*LMOD_PLANNED_BEGIN
-/ * ------------------------------------------------------------------------------------------
- * K5/K8/K9/K12/K14: tcgen05 + TMA GEMM  D[M,N] = A[M,K] * B[N,K]^T (+epilogue), bf16 in, fp32 TMEM
- * accumulate, bf16 out.  Replaces nn.Linear call sites (modeling_qwen2.py:199-200,678-680,726,1176).
- *   trans flags select K-major ('T') vs MN-major ('N') operands so that dgrad / wgrad need no copies.
- *   grouped form: per-expert row ranges from `offsets` (device), weights [E,N,K].
- * /
+/* ------------------------------------------------------------------------------------------
+ * K5/K8/K9/K12/K14: hand-written tcgen05 + TMA GEMM  D[M,N] (+)= A[M,K] * B[N,K]^T, bf16 in, fp32 TMEM accumulate.
+ * Replaces the nn.Linear call sites (modeling_qwen2.py:199-200,678-680,726,1176) and their autograd (dgrad / wgrad).
+ *   a_mn_major / b_mn_major: 0 = operand stored K-major ([rows,K], "T"), 1 = stored MN-major ([K,rows], "N"), so that
+ *   dgrad (B = W as stored) and wgrad (A = dY^T, B = X^T) need no transposed copies.
+ *   epilogue bit0: D = bf16(D + acc).  bias [N] optional.  d_f32_accum != NULL: fp32 D32[M,ldd] += acc instead of D.
+ * Grouped form = DeepSpeed Experts.forward on COMPACT rows (offsets from lmod_moe_route_scatter, 128-row aligned):
+ *   mode 0 fwd  : D[rows_g,N] = A[rows_g,K] * B[g][N,K]^T     mode 1 dgrad: D[rows_g,N] = A[rows_g,K] * B[g][K,N]
+ *   mode 2 wgrad: D[g][M,N] (+)= A[rows_g,M]^T * B[rows_g,N]
+ */
 int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
-                   void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, const void* bias,
-                   const void* residual, int64_t ldr, int epilogue, float* d_f32_accum, void* stream);
-int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t b_expert_stride,
-                           void* D, int64_t ldd, const int32_t* offsets, int E, int64_t max_rows,
-                           int64_t N, int64_t K, int mode, void* stream);
+                   void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, const void* bias, int epilogue,
+                   float* d_f32_accum, void* stream);
+int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+                           const int32_t* offsets, int G, int64_t max_rows, int64_t M, int64_t N, int64_t K,
+                           int mode, int epilogue, void* stream);
 
-/ * K7 attention (modeling_qwen2.py:713-721): causal / non-causal flash attention forward, bf16. * /
-int lmod_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, int64_t batch,
-                  int64_t seq, int nh, int nkv, int hd, int causal, const int32_t* seqlens,
-                  void* out, int64_t ld_o, float* lse, void* stream);
-
+/*LMOD_PLANNED_BEGIN
+ K7 attention (modeling_qwen2.py:713-721): causal / non-causal flash attention forward on tcgen05, bf16.
+ int lmod_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv,
+                   int hd, int causal, const int32_t* seqlens, void* out, int64_t ld_o, float* lse, void* stream);
 LMOD_PLANNED_END*/
 
 #ifdef __cplusplus

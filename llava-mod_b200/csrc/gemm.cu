@@ -1,0 +1,386 @@
+// gemm.cu -- hand-written tcgen05 + TMA GEMM for sm_100a:  D[M,N] (+)= A[M,K] * B[N,K]^T  (bf16 in, fp32 TMEM accumulate)
+//
+// Replaces the nn.Linear call sites of the path (modeling_qwen2.py:199-200 gate/up/down, :678-680 q/k/v, :726 o_proj, :1176
+// lm_head; CLIP / projector linears) and, in its grouped form, DeepSpeed's per-expert loop (Experts.forward) on COMPACT
+// expert rows -- no capacity padding.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0 lane 0 : TMA producer  -- cp.async.bulk.tensor.2d into a 4-stage 128B-swizzled shared-memory ring (A 128x64, B 256x64)
+//   warp 1 lane 0 : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, accumulators in TMEM (2 x 256 columns,
+//                                    double buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue      -- tcgen05.ld 32x32b.x32 -> (+bias) (+D_old) -> bf16 -> 64-byte row segments to global
+//   mbarriers     : full[stage] (TMA complete_tx) / empty[stage] (tcgen05.commit) / tmem_full[2] / tmem_empty[2]
+// Operand "major-ness" is a template parameter, so dgrad (B = W as stored, MN-major) and wgrad (A = dY^T, B = X^T, both MN-major)
+// run without transposes; the UMMA shared-memory descriptors and the TMA boxes change, the pipeline does not.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;            // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+constexpr int GEMM_THREADS = 256;
+constexpr int MAX_GROUPS = 8;
+
+struct GemmParams {
+  __nv_bfloat16* D;
+  const __nv_bfloat16* bias;       // [N] or null
+  float* D32;                      // optional fp32 output (accumulated: D32 += acc) instead of D
+  int64_t ldd;
+  int M, N, K;                     // dense problem (per group for grouped: M is the slab bound)
+  int beta;                        // 1: D = bf16(D + acc)
+  // grouped (experts): row ranges from `offsets` (device), B / D32 advance per group
+  const int32_t* offsets;          // [groups+1] or null
+  int groups;
+  int64_t b_group_rows;            // rows of B per group (N for K-major B) -- B coordinate offset
+  int64_t d_group_stride;          // wgrad grouped: element stride of D per group
+  int wgrad_grouped;               // 1: groups split the REDUCTION (K) range via offsets; M,N dense per group
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t phase) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, phase)) {
+    if (++spins > (1u << 26)) { printf("lmod gemm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+// | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// K-major 128B-swizzled tile (rows x 64 bf16, 128 B per row, 8-row atoms of 1024 B): LBO unused (=1), SBO = 1024; +32 B per UMMA_K
+// MN-major 128B-swizzled tile (64 k-rows x 64 mn per 8 KB block): LBO = 8192 (next 64-wide mn block), SBO = 1024 (next 8 k-rows);
+//   +2048 B per UMMA_K (16 k-rows)
+template <bool MN>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t tile_saddr, int k16) {
+  if (!MN) return smem_desc(tile_saddr + k16 * 32, 16, 1024);
+  return smem_desc(tile_saddr + k16 * 2048, BK * 128, 1024);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format BF16 (1) [7,10) | b_format BF16 (1) [10,13) | a_major [15] | b_major [16]
+// | N>>3 [17,23) | M>>4 [24,29)
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ uint32_t instr_desc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Tile { int m0, n0, kb0, kb1, group, m_end; };
+
+// tile index -> coordinates.  Dense: M fastest (consecutive CTAs share the B tile in L2).  Grouped forward/dgrad: per-group row
+// ranges [offsets[g], offsets[g+1]) (128-row aligned by the router), B rows offset by g*b_group_rows.  Grouped wgrad: each group owns
+// the reduction range [offsets[g], offsets[g+1]) and its own D.
+__device__ __forceinline__ bool get_tile(const GemmParams& p, int t, Tile& o) {
+  const int num_n = (p.N + BN - 1) / BN;
+  if (p.offsets == nullptr) {
+    const int num_m = (p.M + BM - 1) / BM;
+    if (t >= num_m * num_n) return false;
+    o.m0 = (t % num_m) * BM; o.n0 = (t / num_m) * BN; o.kb0 = 0; o.kb1 = (p.K + BK - 1) / BK; o.group = 0; o.m_end = p.M;
+    return true;
+  }
+  if (p.wgrad_grouped) {
+    const int num_m = (p.M + BM - 1) / BM;
+    const int per = num_m * num_n;
+    const int g = t / per;
+    if (g >= p.groups) return false;
+    const int r = t % per;
+    o.m0 = (r % num_m) * BM; o.n0 = (r / num_m) * BN; o.group = g; o.m_end = p.M;
+    o.kb0 = p.offsets[g] / BK; o.kb1 = (p.offsets[g + 1] + BK - 1) / BK;
+    return true;
+  }
+  int base = 0;
+  for (int g = 0; g < p.groups; ++g) {
+    const int r0 = p.offsets[g], r1 = p.offsets[g + 1];
+    const int nm = (r1 - r0 + BM - 1) / BM;
+    const int cnt = nm * num_n;
+    if (t < base + cnt) {
+      const int r = t - base;
+      o.m0 = r0 + (r % nm) * BM; o.n0 = (r / nm) * BN; o.kb0 = 0; o.kb1 = (p.K + BK - 1) / BK; o.group = g; o.m_end = r1;
+      return true;
+    }
+    base += cnt;
+  }
+  return false;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024 B
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_b) : "memory");
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    uint32_t stage = 0, phase = 0;
+    Tile t;
+    for (int ti = blockIdx.x; get_tile(p, ti, t); ti += gridDim.x) {
+      const int b_row0 = (int)(t.group * p.b_group_rows);
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        if (!A_MN) {
+          tma_load_2d(sa, &tma_a, kb * BK, t.m0, &full_bar[stage]);                      // box (64 k, 128 rows)
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tma_a, t.m0 + 64 * j, kb * BK, &full_bar[stage]);   // box (64 mn, 64 k)
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tma_b, kb * BK, b_row0 + t.n0, &full_bar[stage]);             // box (64 k, 256 rows)
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tma_b, t.n0 + 64 * j, b_row0 + kb * BK, &full_bar[stage]);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = instr_desc<A_MN, B_MN>();
+    uint32_t stage = 0, phase = 0, it = 0;
+    Tile t;
+    for (int ti = blockIdx.x; get_tile(p, ti, t); ti += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      uint32_t first = 1;
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        mbar_wait_bounded(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_f16(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        umma_commit(&empty_bar[stage]);                    // frees the smem slot once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full[acc]);                        // accumulator ready for the epilogue
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (TMEM -> registers -> global) =====================
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    uint32_t it = 0;
+    Tile t;
+    for (int ti = blockIdx.x; get_tile(p, ti, t); ti += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      mbar_wait_bounded(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = t.m0 + q * 32 + lane;
+      const bool row_ok = row < t.m_end;
+      const bool empty_k = t.kb1 <= t.kb0;                 // grouped wgrad of an expert with no rows: contributes zero
+      __nv_bfloat16* drow = p.D ? p.D + (p.wgrad_grouped ? t.group * p.d_group_stride : 0) + (int64_t)row * p.ldd : nullptr;
+      float* d32row = p.D32 ? p.D32 + (p.wgrad_grouped ? t.group * p.d_group_stride : 0) + (int64_t)row * p.ldd : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+        const int col0 = t.n0 + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int col = col0 + v * 8;
+          if (col >= p.N) break;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = empty_k ? 0.f : __uint_as_float(r[v * 8 + j]);
+          if (p.bias) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+            f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
+            f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
+          }
+          if (d32row) {
+            float4* o = reinterpret_cast<float4*>(d32row + col);
+            float4 a = o[0], b2 = o[1];
+            a.x += f[0]; a.y += f[1]; a.z += f[2]; a.w += f[3]; b2.x += f[4]; b2.y += f[5]; b2.z += f[6]; b2.w += f[7];
+            o[0] = a; o[1] = b2;
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(drow + col);
+            if (p.beta) {
+              const uint4 old = *o;
+              f[0] += bf16lo(old.x); f[1] += bf16hi(old.x); f[2] += bf16lo(old.y); f[3] += bf16hi(old.y);
+              f[4] += bf16lo(old.z); f[5] += bf16hi(old.z); f[6] += bf16lo(old.w); f[7] += bf16hi(old.w);
+            }
+            uint4 w;
+            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+            *o = w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [outer, inner] matrix with row stride ld (elements), 128B swizzle, zero fill out of bounds
+int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { lmod_set_error("cuTensorMapEncodeTiled entry point not available"); return LMOD_ERR_CUDA; }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { lmod_set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu", (int)r, (unsigned long long)inner,
+                                          (unsigned long long)outer, (unsigned long long)ld); return LMOD_ERR_CUDA; }
+  return LMOD_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int tiles_upper, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    LMOD_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr = true;
+  }
+  int grid = lmod_num_sms();
+  if (tiles_upper < grid) grid = tiles_upper;
+  if (grid < 1) grid = 1;
+  gemm_tcgen05_kernel<A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
+  LMOD_LAUNCH_OK();
+  return LMOD_OK;
+}
+
+int dispatch(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int tiles, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<false, false>(ta, tb, p, tiles, st);
+  if (!a_mn && b_mn) return launch<false, true>(ta, tb, p, tiles, st);
+  if (a_mn && b_mn) return launch<true, true>(ta, tb, p, tiles, st);
+  return launch<true, false>(ta, tb, p, tiles, st);
+}
+
+}  // namespace
+
+// D[M,N] = A * B^T.  a_mn_major = 0: A stored [M,K] (row stride lda) ; 1: A stored [K,M].  b_mn_major = 0: B stored [N,K] ; 1: B stored [K,N].
+// epilogue bit 0: D = bf16(D + acc) ;  d_f32_accum != null: fp32 D32 += acc (ldd applies to it) instead of the bf16 output.
+extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
+                              int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum, void* stream) {
+  LMOD_CHECK_ARG(A && B && (D || d_f32_accum) && M > 0 && N > 0 && K > 0, "lmod_gemm_bf16: null pointer or empty problem");
+  LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0 && N % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) &&
+                 (!D || (uintptr_t)D % 16 == 0), "lmod_gemm_bf16: strides / N must be multiples of 8 elements and pointers 16-byte aligned (TMA)");
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn_major) rc = make_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
+  else rc = make_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+  GemmParams p = {};
+  p.D = (__nv_bfloat16*)D; p.bias = (const __nv_bfloat16*)bias; p.D32 = d_f32_accum; p.ldd = ldd;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.beta = epilogue & 1; p.offsets = nullptr; p.groups = 1;
+  const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN));
+  return dispatch(a_mn_major != 0, b_mn_major != 0, ta, tb, p, tiles, (cudaStream_t)stream);
+}
+
+// Grouped (per-expert) GEMM on rows [offsets[g], offsets[g+1]) (device array; boundaries must be multiples of 128 for mode 0/1, of 64 for
+// mode 2).   mode 0 (forward):  D[rows_g, N] = A[rows_g, K] * B[g][N,K]^T            (A,D [R,*] ; B [G,N,K])
+//            mode 1 (dgrad)  :  D[rows_g, N] = A[rows_g, K] * B[g][K,N]              (B stored [G,K,N], MN-major)
+//            mode 2 (wgrad)  :  D[g][M,N] (+)= A[rows_g, M]^T * B[rows_g, N]         (A stored [R,M], B stored [R,N], both MN-major; reduction
+//                                                                                      over the group's rows)
+extern "C" int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, const int32_t* offsets, int G,
+                                      int64_t max_rows, int64_t M, int64_t N, int64_t K, int mode, int epilogue, void* stream) {
+  LMOD_CHECK_ARG(A && B && D && offsets && G >= 1 && G <= MAX_GROUPS && max_rows > 0, "lmod_grouped_gemm_bf16: bad arguments");
+  LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0 && N % 8 == 0, "lmod_grouped_gemm_bf16: strides / N must be multiples of 8");
+  CUtensorMap ta, tb;
+  GemmParams p = {};
+  p.D = (__nv_bfloat16*)D; p.ldd = ldd; p.beta = epilogue & 1; p.offsets = offsets; p.groups = G;
+  int rc, tiles;
+  if (mode == 0 || mode == 1) {
+    rc = make_map(&ta, A, (uint64_t)K, (uint64_t)max_rows, (uint64_t)lda, BK, BM);
+    if (rc) return rc;
+    if (mode == 0) { rc = make_map(&tb, B, (uint64_t)K, (uint64_t)(G * N), (uint64_t)ldb, BK, BN); p.b_group_rows = N; }
+    else { rc = make_map(&tb, B, (uint64_t)N, (uint64_t)(G * K), (uint64_t)ldb, 64, BK); p.b_group_rows = K; }
+    if (rc) return rc;
+    p.M = (int)max_rows; p.N = (int)N; p.K = (int)K;
+    tiles = (int)(((max_rows + BM - 1) / BM + G) * ((N + BN - 1) / BN));
+    return dispatch(false, mode == 1, ta, tb, p, tiles, (cudaStream_t)stream);
+  }
+  LMOD_CHECK_ARG(mode == 2, "lmod_grouped_gemm_bf16: mode must be 0, 1 or 2");
+  rc = make_map(&ta, A, (uint64_t)M, (uint64_t)max_rows, (uint64_t)lda, 64, BK);
+  if (rc) return rc;
+  rc = make_map(&tb, B, (uint64_t)N, (uint64_t)max_rows, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+  p.M = (int)M; p.N = (int)N; p.K = (int)max_rows; p.wgrad_grouped = 1; p.d_group_stride = M * ldd; p.b_group_rows = 0;
+  tiles = (int)(G * ((M + BM - 1) / BM) * ((N + BN - 1) / BN));
+  return dispatch(true, true, ta, tb, p, tiles, (cudaStream_t)stream);
+}

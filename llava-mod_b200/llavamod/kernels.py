@@ -44,6 +44,40 @@ def mm_tn_acc(dy, x, grad):
         grad.add_(dy.t() @ x)
 
 
+def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, out_f32=None):
+    """Hand-written tcgen05/TMA GEMM (lmod_gemm_bf16).  D[M,N] (+)= A * B^T with
+       a_mn=False: a is [M,K] ; True: a is [K,M]     b_mn=False: b is [N,K] ; True: b is [K,N]."""
+    _need_cuda(a, b)
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N = b.shape[1] if b_mn else b.shape[0]
+    if out_f32 is not None:
+        call("lmod_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), None, out_f32.stride(0), M, N, K, None, 0, ptr(out_f32))
+        return out_f32
+    if out is None:
+        out = torch.empty(M, N, dtype=a.dtype, device=a.device)
+    call("lmod_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0), M, N, K,
+         ptr(bias) if bias is not None else None, 1 if accumulate else 0, None)
+    return out
+
+
+def grouped_gemm(a, b, out, offsets, mode, max_rows=None, accumulate=False):
+    """lmod_grouped_gemm_bf16 on compact expert rows (offsets [G+1] int32 on device, 128-aligned).
+       mode 0: out[R,N] = a[R,K] @ b[G,N,K]^T ; mode 1: out[R,N] = a[R,K] @ b[G,K,N] ; mode 2: out[G,M,N] (+)= a[R,M]^T @ b[R,N] per group."""
+    G = offsets.numel() - 1
+    R = a.shape[0] if max_rows is None else max_rows
+    if mode == 0:
+        N, K = b.shape[1], b.shape[2]
+        call("lmod_grouped_gemm_bf16", ptr(a), a.stride(0), ptr(b), b.stride(1), ptr(out), out.stride(0), ptr(offsets), G, R, 0, N, K, 0, 0)
+    elif mode == 1:
+        K, N = b.shape[1], b.shape[2]
+        call("lmod_grouped_gemm_bf16", ptr(a), a.stride(0), ptr(b), b.stride(1), ptr(out), out.stride(0), ptr(offsets), G, R, 0, N, K, 1, 0)
+    else:
+        M, N = a.shape[1], b.shape[1]
+        call("lmod_grouped_gemm_bf16", ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(1), ptr(offsets), G, R, M, N, 0, 2,
+             1 if accumulate else 0)
+    return out
+
+
 class LinearFn(Function):
     """nn.Linear (modeling_qwen2.py:678-680,726,199-200; CLIP / projector linears).  ``wgrad``/``bgrad`` are views
     of the flat gradient buffer (None when the parameter is frozen); wgrad is accumulated in place."""

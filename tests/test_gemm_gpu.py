@@ -1,0 +1,107 @@
+"""tcgen05/TMA GEMM (lmod_gemm_bf16 / lmod_grouped_gemm_bf16) vs an fp32 reference of the same bf16 inputs.
+Tolerance: the reference accumulates in fp32 as the kernel does (TMEM), so the only difference is the summation order and the
+final bf16 rounding: |err| <= 2^-8 * |ref| + 2^-8 * sqrt(K) * 2e-2."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_mm(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    B = b.float() if b_mn else b.float().t()
+    return A @ B
+
+
+def check(out, ref, K, extra=0.0):
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2.0 ** -8 * (K ** 0.5) * 2e-2 + extra
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4e} (tol {tol.max().item():.4e}), bad {(err > tol).sum().item()} / {err.numel()}"
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (300, 520, 200), (2048, 1024, 1024), (577, 3072, 1024), (64, 8, 72)])
+def test_gemm_all_layouts(M, N, K, a_mn, b_mn):
+    from llavamod import kernels as Kk
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    pad = lambda n: (n + 7) // 8 * 8          # noqa: E731  row strides must be multiples of 8
+    a = torch.randn((K, pad(M)) if a_mn else (M, pad(K)), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((K, pad(N)) if b_mn else (N, pad(K)), device="cuda", generator=g).to(torch.bfloat16)
+    a = a[:, :M] if a_mn else a[:, :K]
+    b = b[:, :N] if b_mn else b[:, :K]
+    out = Kk.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    check(out, ref_mm(a, b, a_mn, b_mn), K)
+
+
+def test_gemm_bias_beta_and_f32_accumulate():
+    from llavamod import kernels as Kk
+    M, N, K = 384, 768, 320
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g).to(torch.bfloat16)
+    ref = ref_mm(a, b, False, False)
+    out = Kk.gemm(a, b, bias=bias)
+    check(out, ref + bias.float(), K)
+    old = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    out2 = Kk.gemm(a, b, out=old.clone(), accumulate=True)
+    check(out2, ref + old.float(), K)
+    acc = torch.ones(M, N, device="cuda")
+    Kk.gemm(a, b, out_f32=acc)
+    torch.testing.assert_close(acc, ref + 1.0, rtol=1e-4, atol=1e-2)
+
+
+def test_grouped_gemm_modes():
+    from llavamod import kernels as Kk
+    G, H, I = 4, 256, 512
+    rows = [256, 0, 384, 128]
+    offs = [0]
+    for r in rows:
+        offs.append(offs[-1] + r)
+    R = offs[-1]
+    offsets = torch.tensor(offs, dtype=torch.int32, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(R + 128, H, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(G, I, H, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    y = torch.zeros(R + 128, I, device="cuda", dtype=torch.bfloat16)
+    Kk.grouped_gemm(x, w, y, offsets, 0)                                   # forward
+    for e in range(G):
+        if rows[e]:
+            check(y[offs[e]:offs[e + 1]], x[offs[e]:offs[e + 1]].float() @ w[e].float().t(), H)
+    assert bool((y[R:] == 0).all())                                        # rows beyond the last group untouched
+    dy = torch.randn(R + 128, I, device="cuda", generator=g).to(torch.bfloat16)
+    dx = torch.zeros(R + 128, H, device="cuda", dtype=torch.bfloat16)
+    Kk.grouped_gemm(dy, w, dx, offsets, 1)                                 # dgrad: dx = dy @ w[e]
+    for e in range(G):
+        if rows[e]:
+            check(dx[offs[e]:offs[e + 1]], dy[offs[e]:offs[e + 1]].float() @ w[e].float(), I)
+    dw = torch.zeros(G, I, H, device="cuda", dtype=torch.bfloat16)
+    Kk.grouped_gemm(dy, x, dw, offsets, 2)                                 # wgrad: dw[e] = dy_e^T @ x_e
+    for e in range(G):
+        ref = dy[offs[e]:offs[e + 1]].float().t() @ x[offs[e]:offs[e + 1]].float()
+        check(dw[e], ref, max(rows[e], 1))
+    dw2 = dw.clone()
+    Kk.grouped_gemm(dy, x, dw2, offsets, 2, accumulate=True)
+    check(dw2[0], 2 * dw[0].float(), rows[0], extra=0.05)
+
+
+def test_gemm_throughput_report():
+    """Not a pass/fail perf gate: prints achieved TFLOP/s of the hand-written kernel next to cuBLAS for the path's big shapes."""
+    from llavamod import kernels as Kk
+    for (M, N, K) in [(2048, 22016, 4096), (2048, 4096, 11008), (2048, 12288, 4096), (2048, 151936, 1024), (2048, 5632, 1024)]:
+        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        res = []
+        for fn in (lambda: Kk.gemm(a, b, out=out), lambda: torch.mm(a, b.t(), out=out)):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res.append(2.0 * M * N * K * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        print(f"GEMM {M}x{N}x{K}: lmod tcgen05 {res[0]:.0f} TFLOP/s, cuBLAS {res[1]:.0f} TFLOP/s")
