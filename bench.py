@@ -287,11 +287,19 @@ def run_ours(args):
 
     # ---- value: device-resident inputs ----
     run(res_batches, args.warmup, False)
+    if args.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            run(res_batches, 1, False)
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    K.TIMERS = {}
     _C.launch_count_reset()
+    trainer.graph_replayed_launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if os.environ.get("LMOD_PROFILE") == "1":          # ncu --profile-from-start off: capture only the timed region
         torch.cuda.cudart().cudaProfilerStart()
@@ -303,8 +311,7 @@ def run_ours(args):
         torch.cuda.cudart().cudaProfilerStop()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _C.launch_count()
-    timers, K.TIMERS = K.TIMERS, None
+    launches = _C.launch_count() + trainer.graph_replayed_launches
     clocks = sampler.finish()
     final_loss = float(last)
     # ---- e2e: host (pinned) buffers through the public trainer call, H2D copies + loss read inside the timed region ----
@@ -319,6 +326,16 @@ def run_ours(args):
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
+    # ---- KL-kernel roofline: the micro-batches of the timed region replay a CUDA graph, where individual kernels cannot be
+    # bracketed by events; so one extra optimizer step runs eagerly right here (same inputs, same kernels, same stream) with CUDA
+    # events around every lmod_kl_fwd_bwd launch.  Not part of `value` / `e2e`.
+    graphs_on = trainer.use_cuda_graphs
+    trainer.use_cuda_graphs = False
+    K.TIMERS = {}
+    run(res_batches, 1, False)
+    torch.cuda.synchronize()
+    timers, K.TIMERS = K.TIMERS, None
+    trainer.use_cuda_graphs = graphs_on
     if world > 1:
         tt = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -356,7 +373,8 @@ def run_ours(args):
         "config": {"workload": wl_name, "student": wl["student"] + "-%dE-top2" % wl["experts"], "teacher": wl["teacher"], "vision": wl["clip"],
                    "seq_len": T, "micro_batch": 1, "grad_accum": accum, "global_batch": accum * world, "loss": "kd_lm (mimic KL + LM + aux)",
                    "parallelism": "dp%d" % world, "l2": "working set per micro-batch (15.4 GB of teacher weights) >> 126 MB L2; no explicit flush",
-                   "gemm": "cuBLAS (library) for plain GEMMs, flash-attn (library) attention; all other ops are liblmod_b200 kernels"},
+                   "gemm": "hand-written tcgen05+TMA GEMM / grouped expert GEMM (liblmod_b200); flash-attn 2 (library) attention; every other op liblmod_b200",
+                   "cuda_graphs": bool(trainer.use_cuda_graphs)},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": accum * (img_bytes + plan_bytes), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -390,6 +408,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
     ap.add_argument("--accum", type=int, default=None, help="profiling aid: override gradient accumulation (micro-batches per step)")
     ap.add_argument("--min-warmup", type=int, default=3)
+    ap.add_argument("--torch-profile", default=None, help="profiling aid: write a per-kernel device-time table of one step to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, args.min_warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -87,10 +87,12 @@ int lmod_align_loss_dense(const float* logp, const float* probs, int64_t ld, con
  *            meta [4+E] fp32 {l_aux, capacity, rows_total, 0, exp_counts...}, xp [2S,H] bf16 permuted.
  *   sync_ws: >= 16 bytes of zero-initialised device scratch (grid barrier), reset by the kernel.
  */
-/* capacity_factor < 0 selects capacity-padded slabs (offsets[e] = e*C, |cf| used) instead of compact rows. */
+/* layout: 0 = compact expert rows ; 1 = capacity-padded slabs (offsets[e] = e*C) ; 2 = compact with every group padded to a
+ * multiple of 128 rows (what lmod_grouped_gemm_bf16 wants; xp must be zero-initialised so padding rows are inert).
+ * meta = {l_aux, capacity, rows_used, rows_end(=offsets[E]), exp_counts[E]}. */
 int lmod_moe_capacity(int64_t S, int E, float capacity_factor, int64_t min_capacity);
 int lmod_moe_route_scatter(const void* x, const float* wg, const float* noise, int64_t S, int64_t H,
-                           int E, float capacity_factor, int64_t min_capacity,
+                           int E, float capacity_factor, int64_t min_capacity, int layout,
                            float* logits, float* gates, int32_t* idx, int32_t* row, float* w,
                            int32_t* offsets, float* meta, void* xp, int32_t* sync_ws, void* stream);
 /* combine einsum("sec,ecm->sm") with bf16-rounded weights + optional residual add (Appendix A step 11,

@@ -18,11 +18,15 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;            // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+// two tile widths: BN = 256 (4-stage ring) for the big GEMMs, BN = 128 (6-stage ring) when a 256-wide tiling would leave SMs idle
+template <int BN> struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+};
 constexpr int GEMM_THREADS = 256;
 constexpr int MAX_GROUPS = 8;
 
@@ -32,7 +36,9 @@ struct GemmParams {
   float* D32;                      // optional fp32 output (accumulated: D32 += acc) instead of D
   int64_t ldd;
   int M, N, K;                     // dense problem (per group for grouped: M is the slab bound)
+  int bn;                          // tile width (256 or 128)
   int beta;                        // 1: D = bf16(D + acc)
+  int splits;                      // split-K factor (>1: fp32 atomic accumulation into D32)
   // grouped (experts): row ranges from `offsets` (device), B / D32 advance per group
   const int32_t* offsets;          // [groups+1] or null
   int groups;
@@ -98,7 +104,7 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t tile_saddr, int k16) {
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format BF16 (1) [7,10) | b_format BF16 (1) [10,13) | a_major [15] | b_major [16]
 // | N>>3 [17,23) | M>>4 [24,29)
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 __device__ __forceinline__ uint32_t instr_desc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
          ((uint32_t)(BM >> 4) << 24);
@@ -110,11 +116,15 @@ struct Tile { int m0, n0, kb0, kb1, group, m_end; };
 // ranges [offsets[g], offsets[g+1]) (128-row aligned by the router), B rows offset by g*b_group_rows.  Grouped wgrad: each group owns
 // the reduction range [offsets[g], offsets[g+1]) and its own D.
 __device__ __forceinline__ bool get_tile(const GemmParams& p, int t, Tile& o) {
+  const int BN = p.bn;
   const int num_n = (p.N + BN - 1) / BN;
   if (p.offsets == nullptr) {
     const int num_m = (p.M + BM - 1) / BM;
-    if (t >= num_m * num_n) return false;
-    o.m0 = (t % num_m) * BM; o.n0 = (t / num_m) * BN; o.kb0 = 0; o.kb1 = (p.K + BK - 1) / BK; o.group = 0; o.m_end = p.M;
+    const int mn = num_m * num_n, nk = (p.K + BK - 1) / BK;
+    if (t >= mn * p.splits) return false;
+    const int ks = t / mn, r = t % mn;                       // output tiles fastest: concurrent CTAs hit different D tiles
+    const int per = (nk + p.splits - 1) / p.splits;
+    o.m0 = (r % num_m) * BM; o.n0 = (r / num_m) * BN; o.kb0 = ks * per; o.kb1 = min(nk, o.kb0 + per); o.group = 0; o.m_end = p.M;
     return true;
   }
   if (p.wgrad_grouped) {
@@ -142,9 +152,10 @@ __device__ __forceinline__ bool get_tile(const GemmParams& p, int t, Tile& o) {
   return false;
 }
 
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -159,7 +170,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_b) : "memory");
   }
-  if (warp == 2) tmem_alloc(&tmem_base_slot, 512);
+  if (warp == 2) tmem_alloc(&tmem_base_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -193,7 +204,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = instr_desc<A_MN, B_MN>();
+    const uint32_t idesc = instr_desc<BN, A_MN, B_MN>();
     uint32_t stage = 0, phase = 0, it = 0;
     Tile t;
     for (int ti = blockIdx.x; get_tile(p, ti, t); ti += gridDim.x, ++it) {
@@ -248,7 +259,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
             f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
           }
-          if (d32row) {
+          if (d32row && p.splits > 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(d32row + col + j, f[j]);
+          } else if (d32row) {
             float4* o = reinterpret_cast<float4*>(d32row + col);
             float4 a = o[0], b2 = o[1];
             a.x += f[0]; a.y += f[1]; a.z += f[2]; a.w += f[3]; b2.x += f[4]; b2.y += f[5]; b2.z += f[6]; b2.w += f[7];
@@ -273,7 +287,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -306,32 +320,42 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, ui
   return LMOD_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int tiles_upper, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    LMOD_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     attr = true;
   }
   int grid = lmod_num_sms();
   if (tiles_upper < grid) grid = tiles_upper;
   if (grid < 1) grid = 1;
-  gemm_tcgen05_kernel<A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM, st>>>(ta, tb, p);
   LMOD_LAUNCH_OK();
   return LMOD_OK;
 }
 
+template <int BN>
+int dispatch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int tiles, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, tiles, st);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, tiles, st);
+  if (a_mn && b_mn) return launch<BN, true, true>(ta, tb, p, tiles, st);
+  return launch<BN, true, false>(ta, tb, p, tiles, st);
+}
 int dispatch(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int tiles, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<false, false>(ta, tb, p, tiles, st);
-  if (!a_mn && b_mn) return launch<false, true>(ta, tb, p, tiles, st);
-  if (a_mn && b_mn) return launch<true, true>(ta, tb, p, tiles, st);
-  return launch<true, false>(ta, tb, p, tiles, st);
+  return p.bn == 256 ? dispatch_bn<256>(a_mn, b_mn, ta, tb, p, tiles, st) : dispatch_bn<128>(a_mn, b_mn, ta, tb, p, tiles, st);
+}
+// 256-wide tiles unless that tiling cannot fill the machine ~1.5 times over
+int pick_bn(int64_t m_tiles, int64_t N) {
+  const int64_t t256 = m_tiles * ((N + 255) / 256);
+  return (t256 >= (int64_t)lmod_num_sms() * 3 / 2 || N <= 128) ? 256 : 128;
 }
 
 }  // namespace
 
 // D[M,N] = A * B^T.  a_mn_major = 0: A stored [M,K] (row stride lda) ; 1: A stored [K,M].  b_mn_major = 0: B stored [N,K] ; 1: B stored [K,N].
-// epilogue bit 0: D = bf16(D + acc) ;  d_f32_accum != null: fp32 D32 += acc (ldd applies to it) instead of the bf16 output.
+// epilogue bit 0: D = bf16(D + acc) ;  d_f32_accum != null: fp32 D32 += acc (ldd applies to it) instead of the bf16 output;
+// epilogue bits 8..: split-K factor (fp32 atomic accumulation into D32, which the caller zero-initialises).
 extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
                               int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum, void* stream) {
   LMOD_CHECK_ARG(A && B && (D || d_f32_accum) && M > 0 && N > 0 && K > 0, "lmod_gemm_bf16: null pointer or empty problem");
@@ -339,6 +363,8 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
                  (!D || (uintptr_t)D % 16 == 0), "lmod_gemm_bf16: strides / N must be multiples of 8 elements and pointers 16-byte aligned (TMA)");
   CUtensorMap ta, tb;
   int rc;
+  const int splits_req = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
+  const int BN = pick_bn(((M + BM - 1) / BM) * splits_req, N);
   if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
   else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
   if (rc) return rc;
@@ -347,8 +373,10 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   if (rc) return rc;
   GemmParams p = {};
   p.D = (__nv_bfloat16*)D; p.bias = (const __nv_bfloat16*)bias; p.D32 = d_f32_accum; p.ldd = ldd;
-  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.beta = epilogue & 1; p.offsets = nullptr; p.groups = 1;
-  const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN));
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.beta = epilogue & 1; p.offsets = nullptr; p.groups = 1; p.bn = BN;
+  p.splits = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
+  LMOD_CHECK_ARG(p.splits == 1 || d_f32_accum, "lmod_gemm_bf16: split-K needs the fp32 accumulate output");
+  const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN)) * p.splits;
   return dispatch(a_mn_major != 0, b_mn_major != 0, ta, tb, p, tiles, (cudaStream_t)stream);
 }
 
@@ -363,8 +391,10 @@ extern "C" int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B,
   LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0 && N % 8 == 0, "lmod_grouped_gemm_bf16: strides / N must be multiples of 8");
   CUtensorMap ta, tb;
   GemmParams p = {};
-  p.D = (__nv_bfloat16*)D; p.ldd = ldd; p.beta = epilogue & 1; p.offsets = offsets; p.groups = G;
+  p.D = (__nv_bfloat16*)D; p.ldd = ldd; p.beta = epilogue & 1; p.offsets = offsets; p.groups = G; p.splits = 1;
   int rc, tiles;
+  const int BN = (mode == 2) ? pick_bn(G * ((M + BM - 1) / BM), N) : pick_bn((max_rows + BM - 1) / BM, N);
+  p.bn = BN;
   if (mode == 0 || mode == 1) {
     rc = make_map(&ta, A, (uint64_t)K, (uint64_t)max_rows, (uint64_t)lda, BK, BM);
     if (rc) return rc;

@@ -361,9 +361,12 @@ extern "C" int lmod_kl_fwd_bwd(const void* s_logits, int64_t ld_s, const void* t
   cfg.blockDim = dim3(KL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cfg.gridDim = dim3(cs);
-  int max_clusters = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_fused_kernel, &cfg);
-  if (e != cudaSuccess || max_clusters <= 0) { (void)cudaGetLastError(); max_clusters = lmod_num_sms() / cs; }
+  static int cached_clusters[2] = {0, 0};        // per cluster size (1 / 8): queried once, outside any stream capture
+  int& max_clusters = cached_clusters[cs == 1 ? 0 : 1];
+  if (max_clusters <= 0) {
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_fused_kernel, &cfg);
+    if (e != cudaSuccess || max_clusters <= 0) { (void)cudaGetLastError(); max_clusters = lmod_num_sms() / cs; }
+  }
   int64_t ncl = n_rows < max_clusters ? n_rows : max_clusters;
   cfg.gridDim = dim3((unsigned)(ncl * cs));
   LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_fused_kernel, p));

@@ -26,7 +26,7 @@ struct RouteParams {
   const float* noise;
   int S, H, E;
   int capacity;
-  int padded;            // 1: offsets[e] = e*capacity (capacity-padded slabs) ; 0: compact rows
+  int layout;            // 0: compact rows ; 1: offsets[e] = e*capacity (capacity-padded slabs) ; 2: compact, groups aligned to 128 rows
   int stage_cap;         // tokens per block whose rows are kept in shared memory across the grid barrier
   float* logits; float* gates; int32_t* idx; int32_t* row; float* w;
   int32_t* offsets; float* meta; __nv_bfloat16* xp;
@@ -152,15 +152,17 @@ __global__ void __launch_bounds__(RT_THREADS, 1) moe_route_scatter_kernel(const 
   }
   __syncthreads();
   if (tid == 0) {
-    int o = 0;
+    int o = 0, used = 0;
     for (int e = 0; e < E; ++e) {
-      s_off[e] = p.padded ? e * p.capacity : o;
-      o += min(s_tot1[e] + s_tot2[e], p.capacity);
+      s_off[e] = (p.layout == 1) ? e * p.capacity : o;
+      int rows_e = min(s_tot1[e] + s_tot2[e], p.capacity);
+      used += rows_e;
+      o += (p.layout == 2) ? ((rows_e + 127) & ~127) : rows_e;
     }
-    s_off[E] = p.padded ? E * p.capacity : o;
+    s_off[E] = (p.layout == 1) ? E * p.capacity : o;
     if (blockIdx.x == 0) {
       for (int e = 0; e <= E; ++e) p.offsets[e] = s_off[e];
-      p.meta[1] = (float)p.capacity; p.meta[2] = (float)o; p.meta[3] = 0.f;
+      p.meta[1] = (float)p.capacity; p.meta[2] = (float)used; p.meta[3] = (float)s_off[E];
       for (int e = 0; e < E; ++e) p.meta[4 + e] = (float)s_tot1[e];
     }
   }
@@ -423,19 +425,18 @@ extern "C" int lmod_moe_capacity(int64_t S, int E, float capacity_factor, int64_
 }
 
 extern "C" int lmod_moe_route_scatter(const void* x, const float* wg, const float* noise, int64_t S, int64_t H, int E,
-                                      float capacity_factor, int64_t min_capacity, float* logits, float* gates,
+                                      float capacity_factor, int64_t min_capacity, int layout, float* logits, float* gates,
                                       int32_t* idx, int32_t* row, float* w, int32_t* offsets, float* meta, void* xp,
                                       int32_t* sync_ws, void* stream) {
   LMOD_CHECK_ARG(x && wg && noise && logits && gates && idx && row && w && offsets && meta && xp && sync_ws,
                  "lmod_moe_route_scatter: null pointer");
   LMOD_CHECK_ARG(E >= 2 && E <= MAXE, "lmod_moe_route_scatter: 2 <= E <= %d required (got %d)", MAXE, E);
   LMOD_CHECK_ARG(S > 0 && H > 0 && H % 8 == 0, "lmod_moe_route_scatter: H must be a multiple of 8");
-  int padded = 0;
-  if (capacity_factor < 0.f) { padded = 1; capacity_factor = -capacity_factor; }   // negative cf selects capacity-padded slabs
+  LMOD_CHECK_ARG(layout >= 0 && layout <= 2, "lmod_moe_route_scatter: layout must be 0 (compact), 1 (capacity slabs) or 2 (compact, 128-aligned)");
   RouteParams p;
   p.x = (const __nv_bfloat16*)x; p.wg = wg; p.noise = noise; p.S = (int)S; p.H = (int)H; p.E = E;
   p.capacity = lmod_moe_capacity(S, E, capacity_factor, min_capacity);
-  p.padded = padded;
+  p.layout = layout;
   p.logits = logits; p.gates = gates; p.idx = idx; p.row = row; p.w = w; p.offsets = offsets; p.meta = meta;
   p.xp = (__nv_bfloat16*)xp; p.sync_ws = (unsigned int*)sync_ws;
 

@@ -27,7 +27,7 @@ SIGNATURES = {
     "lmod_softmax_rows": [_P, _L, _L, _L, _I, _P, _L, _P],
     "lmod_align_loss_dense": [_P, _P, _L, _P, _L, _L, _I, _P, _P, _P],
     "lmod_moe_capacity": [_L, _I, _F, _L],
-    "lmod_moe_route_scatter": [_P, _P, _P, _L, _L, _I, _F, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "lmod_moe_route_scatter": [_P, _P, _P, _L, _L, _I, _F, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "lmod_moe_gather_combine": [_P, _P, _P, _P, _L, _L, _P, _P],
     "lmod_moe_combine_bwd": [_P, _P, _P, _P, _L, _L, _P, _P, _P],
     "lmod_moe_gate_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P],

@@ -26,32 +26,50 @@ def _need_cuda(*ts):
 # GEMM plumbing.  Plain library GEMMs (cuBLAS through torch) for the dense contractions; every fused /
 # irregular op around them is one of our kernels.
 # ---------------------------------------------------------------------------------------------------
+def _rows(t):
+    t2 = t.reshape(-1, t.shape[-1])
+    return t2 if t2.is_contiguous() else t2.contiguous()
+
+
 def mm_nt(x, w, bias=None):
-    """y[M,N] = x[M,K] @ w[N,K]^T (+bias) -- nn.Linear forward."""
-    return torch.nn.functional.linear(x, w, bias)
+    """y[..,N] = x[..,K] @ w[N,K]^T (+bias) -- nn.Linear forward on the tcgen05 GEMM."""
+    y = gemm(_rows(x), w, bias=bias)
+    return y if x.dim() == 2 else y.view(*x.shape[:-1], w.shape[0])     # no view object for the 2-D case (RoPE writes in place)
 
 
 def mm_nn(dy, w):
-    """dx[M,K] = dy[M,N] @ w[N,K] -- nn.Linear dgrad."""
-    return dy @ w
+    """dx[M,K] = dy[M,N] @ w[N,K] -- nn.Linear dgrad: B operand = w as stored (MN-major), no transpose copy.
+    Few output tiles + a very long reduction (lm_head dgrad: K = vocab) -> split-K with fp32 atomics."""
+    dy2 = _rows(dy)
+    M, N = dy2.shape
+    Kout = w.shape[1]
+    tiles = ((M + 127) // 128) * ((Kout + 255) // 256)
+    if tiles < 100 and N >= 16384:
+        split = max(2, min(16, 148 // max(1, tiles)))
+        acc = torch.zeros(M, Kout, dtype=torch.float32, device=dy.device)
+        gemm(dy2, w, b_mn=True, out_f32=acc, split_k=split)
+        return acc.to(dy.dtype)
+    return gemm(dy2, w, b_mn=True)
 
 
 def mm_tn_acc(dy, x, grad):
-    """grad[N,K] += dy[M,N]^T @ x[M,K] -- nn.Linear wgrad accumulated in place into the flat grad buffer."""
-    if grad.dtype == dy.dtype:
-        grad.addmm_(dy.t(), x)
+    """grad[N,K] += dy[M,N]^T @ x[M,K] -- nn.Linear wgrad accumulated in place into the flat grad buffer (both operands MN-major)."""
+    dy2, x2 = _rows(dy), _rows(x)
+    if grad.dtype == torch.float32:
+        gemm(dy2, x2, a_mn=True, b_mn=True, out_f32=grad)
     else:
-        grad.add_(dy.t() @ x)
+        gemm(dy2, x2, a_mn=True, b_mn=True, out=grad, accumulate=True)
 
 
-def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, out_f32=None):
+def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, out_f32=None, split_k=1):
     """Hand-written tcgen05/TMA GEMM (lmod_gemm_bf16).  D[M,N] (+)= A * B^T with
        a_mn=False: a is [M,K] ; True: a is [K,M]     b_mn=False: b is [N,K] ; True: b is [K,N]."""
     _need_cuda(a, b)
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N = b.shape[1] if b_mn else b.shape[0]
     if out_f32 is not None:
-        call("lmod_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), None, out_f32.stride(0), M, N, K, None, 0, ptr(out_f32))
+        call("lmod_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), None, out_f32.stride(0), M, N, K, None,
+             (int(split_k) << 8) if split_k > 1 else 0, ptr(out_f32))
         return out_f32
     if out is None:
         out = torch.empty(M, N, dtype=a.dtype, device=a.device)
@@ -340,10 +358,16 @@ def moe_capacity(S, E, capacity_factor, min_capacity):
     return int(_C.lib().lmod_moe_capacity(S, E, float(capacity_factor), int(min_capacity)))
 
 
-def moe_route_scatter(x, wg, noise, capacity_factor, min_capacity, padded=True):
+LAYOUT_COMPACT, LAYOUT_SLABS, LAYOUT_ALIGNED = 0, 1, 2
+
+
+def moe_route_scatter(x, wg, noise, capacity_factor, min_capacity, layout=LAYOUT_ALIGNED, padded=None):
     """One cooperative launch: fp32 gate GEMV, softmax, top-1 / Gumbel top-2, stable capacity positions,
-    renormalised weights, l_aux, expert offsets and the token scatter.  Returns a dict of device tensors."""
+    renormalised weights, l_aux, expert offsets and the token scatter.  Returns a dict of device tensors.
+    layout: 0 compact rows, 1 capacity-padded [E,C] slabs, 2 compact with 128-row aligned groups (grouped GEMM input)."""
     _need_cuda(x, wg, noise)
+    if padded is not None:
+        layout = LAYOUT_SLABS if padded else LAYOUT_COMPACT
     S, H = x.shape
     E = wg.shape[0]
     C = moe_capacity(S, E, capacity_factor, min_capacity)
@@ -353,11 +377,12 @@ def moe_route_scatter(x, wg, noise, capacity_factor, min_capacity, padded=True):
         idx=torch.empty(S, 2, dtype=torch.int32, device=dev), row=torch.empty(S, 2, dtype=torch.int32, device=dev),
         w=torch.empty(S, 2, dtype=torch.float32, device=dev), offsets=torch.empty(E + 1, dtype=torch.int32, device=dev),
         meta=torch.empty(4 + E, dtype=torch.float32, device=dev), capacity=C)
-    rows = E * C if padded else 2 * S
-    r["xp"] = torch.zeros(rows, H, dtype=x.dtype, device=dev) if padded else torch.empty(rows, H, dtype=x.dtype, device=dev)
-    cf = -float(capacity_factor) if padded else float(capacity_factor)
-    call("lmod_moe_route_scatter", ptr(x), ptr(wg), ptr(noise), S, H, E, cf, int(min_capacity), ptr(r["logits"]), ptr(r["gates"]),
-         ptr(r["idx"]), ptr(r["row"]), ptr(r["w"]), ptr(r["offsets"]), ptr(r["meta"]), ptr(r["xp"]), ptr(_grid_ws(dev)))
+    rows = E * C if layout == LAYOUT_SLABS else (min(2 * S, E * C) + (128 * E if layout == LAYOUT_ALIGNED else 0))
+    r["max_rows"] = rows
+    r["xp"] = torch.zeros(rows, H, dtype=x.dtype, device=dev)      # padding rows must be inert (zero) for the wgrad reduction
+    call("lmod_moe_route_scatter", ptr(x), ptr(wg), ptr(noise), S, H, E, float(capacity_factor), int(min_capacity), int(layout),
+         ptr(r["logits"]), ptr(r["gates"]), ptr(r["idx"]), ptr(r["row"]), ptr(r["w"]), ptr(r["offsets"]), ptr(r["meta"]), ptr(r["xp"]),
+         ptr(_grid_ws(dev)))
     return r
 
 
@@ -370,47 +395,48 @@ def moe_gather_combine(y, row, w, residual=None):
 
 
 class MoEFn(Function):
-    """x: post-attention-layernorm hidden [S,H]; res: residual stream [S,H].  Experts are SwiGLU MLPs with fused
-    gate|up weights w_gu [E,2I,H] and w_dn [E,H,I].  Capacity-padded [E,C,*] slabs feed batched library GEMMs.
-    Returns (res + moe_out, l_aux)."""
+    """x: post-attention-layernorm hidden [S,H]; res: residual stream [S,H].  Experts are SwiGLU MLPs with fused gate|up weights
+    w_gu [E,2I,H] and w_dn [E,H,I].  Expert GEMMs run as ONE grouped tcgen05 GEMM each over COMPACT expert rows (no capacity
+    padding; the reference computes E*C = 1.5x the routed rows).  Returns (res + moe_out, l_aux)."""
 
     @staticmethod
     def forward(ctx, x, res, wg, w_gu, w_dn, noise, cf, min_cap, grads):
         x = _c(x)
         res = _c(res)
         E, I2, H = w_gu.shape
-        r = moe_route_scatter(x, wg, noise, cf, min_cap, padded=True)
-        C = r["capacity"]
-        xp = r["xp"].view(E, C, H)
-        h1 = torch.bmm(xp, w_gu.transpose(1, 2))                       # [E,C,2I]
-        act = silu_mul(h1.detach())                                    # [E,C,I]
-        y = torch.bmm(act, w_dn.transpose(1, 2))                       # [E,C,H]
-        out = moe_gather_combine(y.view(E * C, H), r["row"], r["w"], res)
-        ctx.save_for_backward(x, wg, w_gu, w_dn, r["xp"], h1, act, y, r["row"], r["w"], r["gates"], r["idx"], r["meta"])
+        r = moe_route_scatter(x, wg, noise, cf, min_cap, LAYOUT_ALIGNED)
+        R = r["max_rows"]
+        xp, offs = r["xp"], r["offsets"]
+        h1 = torch.zeros(R, I2, dtype=x.dtype, device=x.device)
+        grouped_gemm(xp, w_gu, h1, offs, 0)                            # [R,2I] = xp @ w_gu[e]^T
+        act = silu_mul(h1)                                             # [R,I]
+        y = torch.zeros(R, H, dtype=x.dtype, device=x.device)
+        grouped_gemm(act, w_dn, y, offs, 0)                            # [R,H] = act @ w_dn[e]^T
+        out = moe_gather_combine(y, r["row"], r["w"], res)
+        ctx.save_for_backward(x, wg, w_gu, w_dn, xp, h1, act, y, r["row"], r["w"], r["gates"], r["idx"], r["meta"], offs)
         ctx.grads = grads
-        ctx.C = C
-        ctx.route = r
         return out, r["meta"][0].clone()
 
     @staticmethod
     def backward(ctx, dout, dlaux):
-        x, wg, w_gu, w_dn, xp, h1, act, y, row, w, gates, idx, meta = ctx.saved_tensors
+        x, wg, w_gu, w_dn, xp, h1, act, y, row, w, gates, idx, meta, offs = ctx.saved_tensors
         E, I2, H = w_gu.shape
-        C = ctx.C
+        R = xp.shape[0]
         S = x.shape[0]
         dout = _c(dout)
-        dy = torch.zeros(E * C, H, dtype=dout.dtype, device=dout.device)
+        dy = torch.zeros(R, H, dtype=dout.dtype, device=dout.device)
         dw = torch.empty(S, 2, dtype=torch.float32, device=dout.device)
         call("lmod_moe_combine_bwd", ptr(dout), ptr(y), ptr(row), ptr(w), S, H, ptr(dy), ptr(dw))
-        dy3 = dy.view(E, C, H)
         g = ctx.grads
-        dact = torch.bmm(dy3, w_dn)                                    # [E,C,I]
+        dact = torch.zeros(R, I2 // 2, dtype=dout.dtype, device=dout.device)
+        grouped_gemm(dy, w_dn, dact, offs, 1)                          # dact = dy @ w_dn[e]
         if g is not None and g.get("w_dn") is not None:
-            g["w_dn"].baddbmm_(dy3.transpose(1, 2), act)               # [E,H,I] +=
+            grouped_gemm(dy, act, g["w_dn"], offs, 2, accumulate=True)  # dW_dn[e] += dy_e^T @ act_e
         dh1 = silu_mul_bwd(dact, h1)
-        dxp = torch.bmm(dh1, w_gu)                                     # [E,C,H]
+        dxp = torch.zeros(R, H, dtype=dout.dtype, device=dout.device)
+        grouped_gemm(dh1, w_gu, dxp, offs, 1)                          # dxp = dh1 @ w_gu[e]
         if g is not None and g.get("w_gu") is not None:
-            g["w_gu"].baddbmm_(dh1.transpose(1, 2), xp.view(E, C, H))
+            grouped_gemm(dh1, xp, g["w_gu"], offs, 2, accumulate=True)  # dW_gu[e] += dh1_e^T @ xp_e
         dlogits = torch.empty(S, E, dtype=torch.float32, device=dout.device)
         gl = None
         if dlaux is not None:
@@ -426,12 +452,14 @@ class MoEFn(Function):
 
 def moe_forward_nograd(x, res, wg, w_gu, w_dn, noise, cf, min_cap):
     E, I2, H = w_gu.shape
-    r = moe_route_scatter(_c(x), wg, noise, cf, min_cap, padded=True)
-    C = r["capacity"]
-    h1 = torch.bmm(r["xp"].view(E, C, H), w_gu.transpose(1, 2))
+    r = moe_route_scatter(_c(x), wg, noise, cf, min_cap, LAYOUT_ALIGNED)
+    R = r["max_rows"]
+    h1 = torch.zeros(R, I2, dtype=x.dtype, device=x.device)
+    grouped_gemm(r["xp"], w_gu, h1, r["offsets"], 0)
     act = silu_mul(h1)
-    y = torch.bmm(act, w_dn.transpose(1, 2))
-    return moe_gather_combine(y.view(E * C, H), r["row"], r["w"], _c(res)), r["meta"][0].clone(), r
+    y = torch.zeros(R, H, dtype=x.dtype, device=x.device)
+    grouped_gemm(act, w_dn, y, r["offsets"], 0)
+    return moe_gather_combine(y, r["row"], r["w"], _c(res)), r["meta"][0].clone(), r
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -504,7 +532,9 @@ class DistillHeadFn(Function):
         dh = mm_nn(dlogits, w_head)
         dh = (dh * g.to(dh.dtype)).reshape(ctx.hshape)
         if ctx.head_grad is not None:
-            ctx.head_grad.add_((dlogits.t() @ h2) * g.to(dlogits.dtype))
+            tmp = torch.zeros_like(ctx.head_grad)
+            mm_tn_acc(dlogits, h2, tmp)
+            ctx.head_grad.add_(tmp * g.to(tmp.dtype))
         return dh, None, None, None, None, None, None, None, None, None
 
 
@@ -548,7 +578,7 @@ class LogpHeadFn(Function):
         d2 = logits.view(B * T, V)
         dh = mm_nn(d2, w_head).view(hidden.shape)
         if ctx.head_grad is not None:
-            ctx.head_grad.add_(d2.t() @ hidden.reshape(B * T, -1))
+            mm_tn_acc(d2, hidden.reshape(B * T, -1), ctx.head_grad)
         return dh, None, None, None
 
 

@@ -265,7 +265,9 @@ class Qwen2Model(nn.Module):
             position_ids = torch.arange(T, device=dev, dtype=torch.int64).unsqueeze(0).expand(B, T)
         pos = position_ids.reshape(-1).to(torch.int64).contiguous()
         cos, sin = self.rope(T, dev, inputs_embeds.dtype)
-        padded = attention_mask is not None and not bool(attention_mask.all())      # _AllTrue (no padding) answers on the host
+        padded = attention_mask is not None and not bool(attention_mask.all())      # MaskInfo answers on the host (no sync)
+        if hasattr(attention_mask, "mask"):
+            attention_mask = attention_mask.mask
         mask4d = _sdpa_mask(attention_mask, B, T, inputs_embeds.dtype) if padded else None
 
         stream = inputs_embeds.reshape(B * T, H)

@@ -65,14 +65,16 @@ def splice_plan(input_ids, attention_mask, labels, n_patches, padding_side="righ
     return src, nl, nm, pos, img
 
 
-class _AllTrue:
-    """Wrapper telling the decoder the mask has no padding without a device sync (``bool(mask.all())`` would sync)."""
+class MaskInfo:
+    """Attention mask + the host-side knowledge whether it contains padding, so the decoder never has to ask the device
+    (``bool(mask.all())`` would be a host sync and would break CUDA-graph capture)."""
 
-    def __init__(self, mask):
+    def __init__(self, mask, all_true):
         self.mask = mask
+        self.all_true = bool(all_true)
 
     def all(self):
-        return True
+        return self.all_true
 
 
 class LlavaMetaModel:
@@ -177,6 +179,6 @@ class LlavaMetaForCausalLM(ABC):
         embeds = K.splice_embed(feats, self.get_model().embed_tokens.weight, plan["src"], plan["img"], n_patches)
         if not plan["has_mask"]:
             new_mask = None
-        else:       # _AllTrue: "no padding" is known on the host, the decoder must not sync to find out
-            new_mask = _AllTrue(plan["mask"]) if plan["all_true"] else plan["mask"]
+        else:       # "no padding" is known on the host, the decoder must not sync to find out
+            new_mask = MaskInfo(plan["mask"], plan["all_true"])
         return None, plan["pos"], new_mask, past_key_values, embeds, (plan["labels"] if plan["has_labels"] else None)

@@ -157,8 +157,45 @@ class AlignTrainer(BaseTrainer):
         return losses.mean()
 
     def store_metrics(self, metrics: Dict[str, float], train_eval: Literal["train", "eval"] = "train") -> None:
+        if self._suppress_store:          # graph capture: the static output tensors are cloned after every replay instead
+            return
         for key, value in metrics.items():
             self._stored_metrics[train_eval][key].append(value)
+
+    # ---- CUDA-graph plumbing (see BaseTrainer._graphed_micro_batch) -------------------------------------------------
+    def _graph_signature(self, inputs):
+        images = inputs.get("images")
+        if images is None or inputs.get("moe_noise") is not None:
+            return None
+        ids = inputs["input_ids"]
+        plan = inputs.get("splice_plan")
+        if plan is None:
+            plan = self.model.make_splice_plan(ids, inputs.get("attention_mask"), inputs["labels"])
+            inputs["splice_plan"] = plan
+        if not self.share_tower or not plan["all_true"]:
+            return None                   # padded batches take the masked-attention path eagerly
+        n_img = len(images) if not torch.is_tensor(images) else images.shape[0]
+        ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
+        return ("align", tuple(ids.shape), tuple(plan["src"].shape), n_img, ish, plan["has_mask"], plan["has_labels"], self.loss_type)
+
+    def _graph_static_inputs(self, inputs, static):
+        dev = self.model.device
+        images, plan = inputs["images"], inputs["splice_plan"]
+        if static is None:
+            n = len(images) if not torch.is_tensor(images) else images.shape[0]
+            ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
+            static = dict(input_ids=inputs["input_ids"], labels=inputs["labels"], attention_mask=inputs.get("attention_mask"),
+                          images=torch.empty((n,) + ish, dtype=self.model.dtype, device=dev),
+                          splice_plan={k: (torch.empty_like(v) if torch.is_tensor(v) else v) for k, v in plan.items()})
+        if torch.is_tensor(images):
+            static["images"].copy_(images, non_blocking=True)
+        else:
+            for i, im in enumerate(images):
+                static["images"][i].copy_(im, non_blocking=True)
+        for k, v in plan.items():
+            if torch.is_tensor(v):
+                static["splice_plan"][k].copy_(v, non_blocking=True)
+        return static
 
     def log(self, logs: Dict[str, float]) -> None:
         train_eval = "train" if "loss" in logs else "eval"

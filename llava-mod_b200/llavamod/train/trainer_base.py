@@ -42,6 +42,12 @@ class BaseTrainer:
         self.rank = dist.get_rank() if self.world_size > 1 else 0
         self._accum = 0
         self._total_steps = None
+        # CUDA graphs: the forward+backward of a micro-batch is captured once per input signature and replayed, which
+        # removes the per-launch host cost (~1000 launches per micro-batch) -- "CUDA streams and graphs instead of a tracing compiler"
+        self.use_cuda_graphs = bool(int(os.environ.get("LLAVAMOD_CUDA_GRAPHS", "1")))
+        self._graphs = {}
+        self._suppress_store = False
+        self.graph_replayed_launches = 0     # liblmod kernels executed through graph replays (not seen by the host-side counter)
 
     # ---- optimizer ---------------------------------------------------------------------------------------
     def create_optimizer(self):
@@ -82,14 +88,55 @@ class BaseTrainer:
         model.train()
         if self._accum == 0:
             opt.zero_grad()
-        loss = self.compute_loss(model, inputs)
-        loss.backward()
+        loss = None
+        if self.use_cuda_graphs and hasattr(self, "_graph_signature"):
+            loss = self._graphed_micro_batch(model, inputs)
+        if loss is None:
+            loss = self.compute_loss(model, inputs)
+            loss.backward()
         self._accum += 1
         if self._accum == self.args.gradient_accumulation_steps:
             opt.step(lr=self.current_lr(), grad_scale=1.0 / (self._accum * self.world_size))
             self._accum = 0
             self.state.global_step += 1
         return loss.detach()
+
+    # ---- CUDA-graph replay of one micro-batch ----------------------------------------------------------------------
+    def _graphed_micro_batch(self, model, inputs):
+        """Returns the loss tensor (detached, static buffer clone) or None when this batch must run eagerly.
+        Subclasses provide ``_graph_signature(inputs)`` (hashable, or None = not capturable) and
+        ``_graph_static_inputs(inputs, static=None)`` (allocate / refill the static device inputs)."""
+        import torch
+        sig = self._graph_signature(inputs)
+        if sig is None:
+            return None
+        ent = self._graphs.get(sig)
+        if ent is None:
+            ent = self._graphs[sig] = {"warm": 0}
+        if "graph" not in ent:
+            ent["warm"] += 1
+            if ent["warm"] <= 2:                         # eager warm-up (lazy init, autotune, workspace allocation)
+                return None
+            static = self._graph_static_inputs(inputs, None)
+            torch.cuda.synchronize()
+            from .. import _C
+            g = torch.cuda.CUDAGraph()
+            self._suppress_store = True
+            n0 = _C.launch_count()
+            try:
+                with torch.cuda.graph(g):
+                    loss, outputs = self.compute_loss(model, static, return_outputs=True)
+                    loss.backward()
+            finally:
+                self._suppress_store = False
+            ent.update(graph=g, static=static, loss=loss.detach(), outputs={k: v for k, v in outputs.items()},
+                       launches=_C.launch_count() - n0)
+            # the capture pass does not execute: fall through to a replay for this very batch
+        self._graph_static_inputs(inputs, ent["static"])
+        ent["graph"].replay()
+        self.graph_replayed_launches += ent["launches"]
+        self.store_metrics({k: (v.clone() if hasattr(v, "clone") else v) for k, v in ent["outputs"].items()}, train_eval="train")
+        return ent["loss"].clone()
 
     # ---- loop ------------------------------------------------------------------------------------------------
     def get_train_dataloader(self):

@@ -153,14 +153,16 @@ def test_dense_compat_kernels():
 # MoE router / scatter / combine
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("S,H,E,cf,padded", [(64, 128, 4, 1.5, True), (333, 256, 4, 1.0, False), (2048, 1024, 4, 1.5, True),
-                                             (500, 128, 8, 0.5, False), (16, 64, 2, 2.0, True)])
+                                             (500, 128, 8, 0.5, False), (16, 64, 2, 2.0, True), (2048, 1024, 4, 1.5, "aligned"),
+                                             (700, 128, 4, 0.75, "aligned")])
 def test_route_scatter_bit_exact(S, H, E, cf, padded):
     from llavamod import kernels as K
     g = torch.Generator().manual_seed(S + E)
     x = torch.randn(S, H, generator=g).to(torch.bfloat16)
     wg = torch.randn(E, H, generator=g) * 0.2
     noise = R.gumbel_noise((S, E), g)
-    r = K.moe_route_scatter(x.to(dev()), wg.to(dev()), noise.to(dev()), cf, 0, padded=padded)
+    layout = K.LAYOUT_ALIGNED if padded == "aligned" else (K.LAYOUT_SLABS if padded else K.LAYOUT_COMPACT)
+    r = K.moe_route_scatter(x.to(dev()), wg.to(dev()), noise.to(dev()), cf, 0, layout=layout)
     torch.cuda.synchronize()
     logits = r["logits"].cpu()
     torch.testing.assert_close(logits, x.float() @ wg.t(), rtol=1e-4, atol=1e-4)        # fp32 gate GEMV, different sum order
@@ -182,7 +184,14 @@ def test_route_scatter_bit_exact(S, H, E, cf, padded):
     meta = r["meta"].cpu()
     assert abs(meta[0].item() - o["l_aux"].item()) < 1e-5 * abs(o["l_aux"].item())
     assert torch.equal(meta[4:4 + E].long(), o["exp_counts"])
-    if padded:
+    if padded == "aligned":
+        cnt = torch.minimum(torch.bincount(idx[:, 0], minlength=E) + torch.bincount(idx[:, 1], minlength=E), torch.tensor(C))
+        assert bool((off % 128 == 0).all()) and torch.equal(off[1:] - off[:-1], (cnt + 127) // 128 * 128)
+        assert int(meta[2].item()) == int(cnt.sum()) and int(meta[3].item()) == int(off[-1]) and off[-1] <= r["xp"].shape[0]
+        unused = torch.ones(r["xp"].shape[0], dtype=torch.bool)
+        unused[torch.cat([row[:, 0][keep1], row[:, 1][keep2]])] = False
+        assert bool((r["xp"].cpu()[unused] == 0).all())                  # padding rows stay zero (inert in the grouped wgrad)
+    elif padded:
         assert torch.equal(off, torch.arange(E + 1) * C)
     else:
         cnt = torch.minimum(torch.bincount(idx[:, 0], minlength=E) + torch.bincount(idx[:, 1], minlength=E), torch.tensor(C))
