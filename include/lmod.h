@@ -172,11 +172,13 @@ int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ld
                            const int32_t* offsets, int G, int64_t max_rows, int64_t M, int64_t N, int64_t K,
                            int mode, int epilogue, void* stream);
 
-/*LMOD_PLANNED_BEGIN
- K7 attention (modeling_qwen2.py:713-721): causal / non-causal flash attention forward on tcgen05, bf16.
- int lmod_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv,
-                   int hd, int causal, const int32_t* seqlens, void* out, int64_t ld_o, float* lse, void* stream);
-LMOD_PLANNED_END*/
+/* ------------------------------------------------------------------------------------------
+ * K7: flash-attention FORWARD on tcgen05/TMEM/TMA (modeling_qwen2.py:713-721 causal; CLIP non-causal), reading the fused RoPE'd
+ * QKV buffer [batch*seq, (nh+2*nkv)*hd] in place (GQA by index).  hd in {64,128}.  out [batch*seq, nh*hd];
+ * lse [batch, nh, seq] fp32 (natural-log LSE of the scaled scores -- what flash-attn's backward consumes) or NULL. */
+int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
+                  float softmax_scale, void* out, int64_t ld_o, float* lse, void* stream);
+
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,252 @@
+// attn.cu -- flash-attention FORWARD on tcgen05 / TMEM / TMA (sm_100a), bf16 in, fp32 softmax + accumulation.
+//
+// Replaces F.scaled_dot_product_attention of Qwen2SdpaAttention.forward (modeling_qwen2.py:713-721, causal, no padding) and the CLIP
+// tower's non-causal self-attention (transformers CLIPVisionModel via clip_encoder.py:54).  Operates directly on the fused, RoPE'd
+// QKV projection output [B*T, (nh + 2*nkv)*hd] -- no head transposes, GQA by index (repeat_kv :204-213 never materialises).
+//
+// One CTA = one (batch, head, 128-query block); two CTAs are co-resident per SM so one CTA's softmax overlaps the other's MMAs.
+//   warp 0 lane 0 : TMA producer -- Q tile once, K/V blocks of 64 keys through a 2-stage 128B-swizzled ring
+//   warp 1 lane 0 : MMA issuer   -- S_j = Q K_j^T (SS, M=128 N=64 K=16 x hd/16) into one of two S buffers in TMEM;
+//                                   O += P_j V_j (TS: A = P_j read from TMEM, B = V_j MN-major from smem, N = hd)
+//   warps 2..5    : softmax      -- one thread per query row (TMEM lane): tcgen05.ld S row -> scale, causal / length mask, running max,
+//                                   exp2, row sum -> P (bf16x2) written back over S with tcgen05.st; O rescaled in TMEM when the running
+//                                   max moved (skipped warp-uniformly when it did not); epilogue O / l -> bf16 -> global, LSE
+// TMEM columns: S0 | S1 (64 each, P aliases its S) | O (hd).  All tensor-core work is issued by a single thread; tcgen05 executes MMAs in
+// issue order, which is what makes the S/P aliasing safe (S_{j+2} is issued after P_j V_j).
+#include "tc05.cuh"
+
+namespace {
+
+constexpr int BQ = 128, BKV = 64;
+constexpr int ATT_THREADS = 192;
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  float* lse;            // [B, nh, T] natural-log LSE of the scaled scores (flash-attn's softmax_lse), may be null
+  int64_t ld_o;
+  int B, T, nh, nkv;
+  int causal;
+  float scale_log2;      // softmax_scale * log2(e)
+};
+
+// instruction descriptor: F32 accumulate, BF16 inputs, M = 128, N = n ; b_mn selects the B major-ness
+__device__ __forceinline__ uint32_t attn_idesc(int n, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnParams p) {
+  constexpr int KSUB = HD / 64;                       // 64-column sub-tiles along the head dimension
+  constexpr int Q_BYTES = BQ * HD * 2;
+  constexpr int K_BYTES = BKV * HD * 2, V_BYTES = BKV * HD * 2;
+  constexpr int TMEM_COLS = (2 * BKV + HD <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], p_full[2], pv_done;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + Q_BYTES;                      // stage s: K at sKV + s*(K+V), V right after
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // heavier (later) causal query blocks first
+  const int nqb = (p.T + BQ - 1) / BQ;
+  const int qb = p.causal ? (nqb - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.nh / p.nkv);
+  const int q0 = qb * BQ;
+  const int kv_len = p.causal ? min(p.T, q0 + BQ) : p.T;
+  const int nblk = (kv_len + BKV - 1) / BKV;
+  const int row_base = b * p.T;                       // row of token 0 of this batch in the fused buffer
+  const int col_q = h * HD, col_k = (p.nh + hk) * HD, col_v = (p.nh + p.nkv + hk) * HD;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); }
+    mbar_init(&pv_done, 1);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_kv) : "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tS0 = tmem, tO = tmem + 2 * BKV;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(&q_full, Q_BYTES);
+#pragma unroll
+    for (int i = 0; i < KSUB; ++i) tma_load_2d(sQ + i * (BQ * 128), &tma_q, col_q + 64 * i, row_base + q0, &q_full);
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait_bounded(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      uint8_t* sK = sKV + s * (K_BYTES + V_BYTES);
+      uint8_t* sV = sK + K_BYTES;
+      mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+#pragma unroll
+      for (int i = 0; i < KSUB; ++i) {
+        tma_load_2d(sK + i * (BKV * 128), &tma_kv, col_k + 64 * i, row_base + j * BKV, &kv_full[s]);
+        tma_load_2d(sV + i * (BKV * 128), &tma_kv, col_v + 64 * i, row_base + j * BKV, &kv_full[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_qk = attn_idesc(BKV, false), idesc_pv = attn_idesc(HD, true);
+    const uint32_t aQ = smem_u32(sQ);
+    auto issue_qk = [&](int j) {
+      const int s = j & 1;
+      mbar_wait_bounded(&kv_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sKV + s * (K_BYTES + V_BYTES));
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {
+        const uint64_t da = smem_desc(aQ + (k / 4) * (BQ * 128) + (k % 4) * 32, 16, 1024);
+        const uint64_t db = smem_desc(aK + (k / 4) * (BKV * 128) + (k % 4) * 32, 16, 1024);
+        umma_f16(tS0 + s * BKV, da, db, idesc_qk, k > 0 ? 1u : 0u);
+      }
+      umma_commit(&s_full[s]);
+    };
+    mbar_wait_bounded(&q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      if (j + 1 < nblk) issue_qk(j + 1);              // tensor core works on S_{j+1} while the softmax warps chew on S_j
+      mbar_wait_bounded(&p_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aV = smem_u32(sKV + s * (K_BYTES + V_BYTES) + K_BYTES);
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k) {
+        // V_j as B operand, MN-major: 64-wide hd blocks BKV*128 B apart (LBO), 8-key groups 1024 B apart (SBO), 16 keys = 2048 B per MMA
+        const uint64_t db = smem_desc(aV + k * 2048, BKV * 128, 1024);
+        umma_f16_ts(tO, tS0 + s * BKV + k * 8, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);     // P: 16 bf16 = 8 TMEM columns per MMA
+      }
+      umma_commit(&kv_empty[s]);
+      umma_commit(&pv_done);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax / correction / epilogue: one thread per query row =====================
+    const int q = warp & 3;                           // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;                      // row within the query block == TMEM lane
+    const int qrow = q0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait_bounded(&s_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[BKV];
+      tmem_ld32(tS0 + s * BKV + lane_off, sv);
+      tmem_ld32(tS0 + s * BKV + 32 + lane_off, sv + 32);
+      const int kv0 = j * BKV;
+      const bool need_mask = (p.causal && kv0 + BKV - 1 > q0) || (kv0 + BKV > p.T);
+      float mx = m;
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) {
+        float x = __uint_as_float(sv[c]) * p.scale_log2;
+        if (need_mask) {
+          const int kv = kv0 + c;
+          if (kv >= p.T || (p.causal && kv > qrow)) x = -INFINITY;
+        }
+        sv[c] = __float_as_uint(x);
+        mx = fmaxf(mx, x);
+      }
+      const float m_use = (mx == -INFINITY) ? 0.f : mx;     // fully masked row (only rows >= T): keep everything finite
+      const float alpha = ex2f(m - m_use);                   // m = -inf on the first block -> 0
+      float rs = 0.f;
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 2) {
+        const float p0 = ex2f(__uint_as_float(sv[c]) - m_use), p1 = ex2f(__uint_as_float(sv[c + 1]) - m_use);
+        rs += p0 + p1;
+        pk[c >> 1] = pack_bf16x2(p0, p1);
+      }
+      l = l * alpha + rs;
+      const bool moved = mx > m;
+      m = mx;
+      if (j > 0) {
+        mbar_wait_bounded(&pv_done, (j - 1) & 1);            // O holds blocks 0..j-1
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, moved)) {                // rescale O only when some row of this warp raised its max
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32 + lane_off, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + c * 32 + lane_off, o);
+          }
+        }
+      }
+      tmem_st32(tS0 + s * BKV + lane_off, pk);               // P_j over the first 32 columns of S_j
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[s]);
+    }
+    // ---- epilogue ----
+    mbar_wait_bounded(&pv_done, (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv = (l > 0.f) ? 1.f / l : 0.f;
+    const bool ok = qrow < p.T;
+    __nv_bfloat16* orow = p.out + (int64_t)(row_base + qrow) * p.ld_o + col_q;
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32 + lane_off, o);
+      if (ok) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv, __uint_as_float(o[v * 8 + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv, __uint_as_float(o[v * 8 + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv, __uint_as_float(o[v * 8 + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv, __uint_as_float(o[v * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + v * 8) = w;
+        }
+      }
+    }
+    if (ok && p.lse) p.lse[((int64_t)b * p.nh + h) * p.T + qrow] = (m + lg2f(l)) * LN2_F;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int HD>
+int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
+  constexpr int SMEM = BQ * HD * 2 + 2 * (2 * BKV * HD * 2) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  dim3 grid((p.T + BQ - 1) / BQ, p.nh, p.B);
+  attn_fwd_kernel<HD><<<grid, ATT_THREADS, SMEM, st>>>(tq, tkv, p);
+  LMOD_LAUNCH_OK();
+  return LMOD_OK;
+}
+
+}  // namespace
+
+// qkv: fused projection output [batch*seq, (nh + 2*nkv)*hd] bf16 (q heads | k heads | v heads), row stride ld_qkv.
+// out: [batch*seq, nh*hd] (row stride ld_o).  lse: [batch, nh, seq] fp32 or NULL.  hd in {64, 128}.
+extern "C" int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
+                             float softmax_scale, void* out, int64_t ld_o, float* lse, void* stream) {
+  LMOD_CHECK_ARG(qkv && out && batch > 0 && seq > 0 && nh > 0 && nkv > 0 && nh % nkv == 0, "lmod_attn_fwd: bad arguments");
+  LMOD_CHECK_ARG(hd == 64 || hd == 128, "lmod_attn_fwd: head_dim %d not built (64 and 128 are)", hd);
+  LMOD_CHECK_ARG(ld_qkv % 8 == 0 && ld_o % 8 == 0 && ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), "lmod_attn_fwd: alignment");
+  CUtensorMap tq, tkv;
+  const uint64_t cols = (uint64_t)(nh + 2 * nkv) * hd, rows = (uint64_t)(batch * seq);
+  int rc = make_map(&tq, qkv, cols, rows, (uint64_t)ld_qkv, 64, BQ);
+  if (rc) return rc;
+  rc = make_map(&tkv, qkv, cols, rows, (uint64_t)ld_qkv, 64, BKV);
+  if (rc) return rc;
+  AttnParams p;
+  p.out = (__nv_bfloat16*)out; p.lse = lse; p.ld_o = ld_o; p.B = (int)batch; p.T = (int)seq; p.nh = nh; p.nkv = nkv; p.causal = causal;
+  p.scale_log2 = softmax_scale * LOG2E_F;
+  return hd == 128 ? launch_attn<128>(tq, tkv, p, (cudaStream_t)stream) : launch_attn<64>(tq, tkv, p, (cudaStream_t)stream);
+}

@@ -128,6 +128,51 @@ def linear(x, w, bias=None, wgrad=None, bgrad=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+# attention (K7)
+# ---------------------------------------------------------------------------------------------------
+ATTN_HEAD_DIMS = (64, 128)
+
+
+def attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale=None, need_lse=False):
+    """Hand-written tcgen05 flash-attention forward on the fused QKV buffer [B*T, (nh+2nkv)*hd] -> [B*T, nh*hd] (+ lse [B,nh,T])."""
+    _need_cuda(qkv)
+    out = torch.empty(B * T, nh * hd, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(B, nh, T, dtype=torch.float32, device=qkv.device) if need_lse else None
+    call("lmod_attn_fwd", ptr(qkv), qkv.stride(0), B, T, nh, nkv, hd, 1 if causal else 0, float(scale if scale is not None else hd ** -0.5),
+         ptr(out), out.stride(0), ptr(lse) if lse is not None else None)
+    return out, lse
+
+
+class AttnFn(Function):
+    """Qwen2SdpaAttention core (modeling_qwen2.py:713-721).  Forward: our tcgen05 kernel.  Backward (student only): flash-attn 2's
+    library backward fed with our output and log-sum-exp, writing dq|dk|dv straight into one fused gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, T, nh, nkv, hd, causal, scale):
+        scale = float(scale if scale is not None else hd ** -0.5)
+        out, lse = attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale, need_lse=True)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.dims = (B, T, nh, nkv, hd, causal, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from flash_attn.flash_attn_interface import _wrapped_flash_attn_backward
+        qkv, out, lse = ctx.saved_tensors
+        B, T, nh, nkv, hd, causal, scale = ctx.dims
+        q = qkv[:, : nh * hd].view(B, T, nh, hd)
+        k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)
+        v = qkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd)
+        dqkv = torch.empty_like(qkv)
+        dq = dqkv[:, : nh * hd].view(B, T, nh, hd)
+        dk = dqkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)
+        dv = dqkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd)
+        _wrapped_flash_attn_backward(_c(dout).view(B, T, nh, hd), q, k, v, out.view(B, T, nh, hd), lse, dq, dk, dv, 0.0, scale, bool(causal),
+                                     -1, -1, 0.0, None, False, rng_state=None)
+        return dqkv, None, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
 # norms / rope / activations
 # ---------------------------------------------------------------------------------------------------
 class RMSNormFn(Function):

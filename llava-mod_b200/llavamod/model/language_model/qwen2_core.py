@@ -334,11 +334,16 @@ def _sdpa_mask(attention_mask, B, T, dtype):
 
 def _attention(qkv, B, T, nh, nkv, hd, mask4d, causal=True, scale=None):
     """K7: causal self-attention on the fused, RoPE'd QKV buffer [B*T, (nh+2nkv)*hd] -> [B*T, nh*hd].
-    Library attention (flash-attn 2 / SDPA) in this round; the tcgen05 kernel is the planned replacement."""
+    head_dim 64 / 128 without padding: our tcgen05 forward (lmod_attn_fwd), flash-attn 2 library backward for the student.
+    Padded batches: SDPA with the reference's additive mask.  Other head dims: flash-attn 2 library."""
     q = qkv[:, : nh * hd].view(B, T, nh, hd)
     k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)
     v = qkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd)
-    if mask4d is None:
+    if mask4d is None and hd in K.ATTN_HEAD_DIMS:
+        if torch.is_grad_enabled() and qkv.requires_grad:
+            return K.AttnFn.apply(qkv, B, T, nh, nkv, hd, causal, scale)
+        return K.attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale)[0]
+    if mask4d is None:          # head dims the tcgen05 kernel is not built for (tiny test configs): library attention
         from flash_attn import flash_attn_func
         o = flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=scale, causal=causal)
         return o.reshape(B * T, nh * hd)

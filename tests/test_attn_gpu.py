@@ -1,0 +1,73 @@
+"""tcgen05 flash-attention forward (lmod_attn_fwd) vs fp32 SDPA on the same bf16 inputs.
+Tolerance: P is rounded to bf16 before P*V (as flash-attn 2 does) -> |err| <= 2^-7 * max|out| ; lse within 1e-3."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_attn(qkv, B, T, nh, nkv, hd, causal, scale):
+    q = qkv[:, : nh * hd].view(B, T, nh, hd).transpose(1, 2).float()
+    k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd).transpose(1, 2).float()
+    v = qkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd).transpose(1, 2).float()
+    rep = nh // nkv
+    k = k.repeat_interleave(rep, 1)
+    v = v.repeat_interleave(rep, 1)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        s = s.masked_fill(torch.ones(T, T, dtype=torch.bool, device=s.device).triu(1), float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    o = torch.softmax(s, -1) @ v
+    return o.transpose(1, 2).reshape(B * T, nh * hd), lse
+
+
+@pytest.mark.parametrize("B,T,nh,nkv,hd,causal", [(1, 128, 2, 2, 64, True), (1, 256, 2, 2, 128, True), (2, 300, 4, 2, 64, True),
+                                                  (1, 577, 4, 4, 64, False), (2, 1024, 4, 4, 128, True), (1, 2048, 8, 2, 128, True),
+                                                  (3, 64, 2, 1, 128, False), (1, 2048, 16, 16, 64, True)])
+def test_attn_fwd_matches_sdpa(B, T, nh, nkv, hd, causal):
+    from llavamod import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(T + nh + hd)
+    qkv = torch.randn(B * T, (nh + 2 * nkv) * hd, device="cuda", generator=g).to(torch.bfloat16)
+    scale = hd ** -0.5
+    out, lse = K.attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale, need_lse=True)
+    torch.cuda.synchronize()
+    ref, ref_lse = ref_attn(qkv, B, T, nh, nkv, hd, causal, scale)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2.0 ** -7 * ref.abs().max().item() + 1e-3, err
+    torch.testing.assert_close(lse, ref_lse, rtol=1e-3, atol=1e-3)
+
+
+def test_attn_backward_through_library_bwd():
+    from llavamod import kernels as K
+    B, T, nh, nkv, hd = 2, 384, 4, 2, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = torch.randn(B * T, (nh + 2 * nkv) * hd, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True)
+    out = K.AttnFn.apply(qkv, B, T, nh, nkv, hd, True, None)
+    go = torch.randn(B * T, nh * hd, device="cuda", generator=g).to(torch.bfloat16)
+    out.backward(go)
+    x = qkv.detach().float().requires_grad_(True)
+    ref, _ = ref_attn(x, B, T, nh, nkv, hd, True, hd ** -0.5)
+    ref.backward(go.float())
+    rel = (qkv.grad.float() - x.grad).norm().item() / x.grad.norm().item()
+    assert rel < 2e-2, rel
+
+
+def test_attn_throughput_report():
+    from llavamod import kernels as K
+    from flash_attn import flash_attn_func
+    for (B, T, nh, hd, causal) in [(1, 2048, 32, 128, True), (1, 2048, 16, 64, True), (1, 577, 16, 64, False), (4, 4096, 32, 128, True)]:
+        qkv = torch.randn(B * T, 3 * nh * hd, device="cuda").to(torch.bfloat16)
+        q, k, v = [qkv[:, i * nh * hd:(i + 1) * nh * hd].view(B, T, nh, hd) for i in range(3)]
+        fl = 4.0 * B * nh * T * T * hd * (0.5 if causal else 1.0)
+        res = []
+        for fn in (lambda: K.attention_fwd(qkv, B, T, nh, nh, hd, causal), lambda: flash_attn_func(q, k, v, causal=causal)):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res.append(fl * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        print(f"attn fwd B{B} T{T} nh{nh} hd{hd} causal={causal}: lmod tcgen05 {res[0]:.0f} TFLOP/s, flash-attn2 {res[1]:.0f} TFLOP/s")
