@@ -373,7 +373,7 @@ def run_ours(args):
         "config": {"workload": wl_name, "student": wl["student"] + "-%dE-top2" % wl["experts"], "teacher": wl["teacher"], "vision": wl["clip"],
                    "seq_len": T, "micro_batch": 1, "grad_accum": accum, "global_batch": accum * world, "loss": "kd_lm (mimic KL + LM + aux)",
                    "parallelism": "dp%d" % world, "l2": "working set per micro-batch (15.4 GB of teacher weights) >> 126 MB L2; no explicit flush",
-                   "gemm": "hand-written tcgen05+TMA GEMM / grouped expert GEMM (liblmod_b200); flash-attn 2 (library) attention; every other op liblmod_b200",
+                   "gemm": "hand-written tcgen05+TMA GEMM / grouped expert GEMM and tcgen05 flash-attention forward (liblmod_b200); flash-attn 2 library only for the student attention BACKWARD; every other op liblmod_b200",
                    "cuda_graphs": bool(trainer.use_cuda_graphs)},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": accum * (img_bytes + plan_bytes), "d2h_bytes_per_step": 4,

@@ -1,0 +1,69 @@
+"""Stand-alone launches of the hot kernels at config-2 shapes, small enough in memory for `ncu --set full` to replay cheaply.
+    ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05|attn_fwd|kl_fused|moe_route' -o gpurun_out/kernels_rN python profiles/microbench.py
+Also prints CUDA-event timings (TFLOP/s, GB/s) when run without ncu."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "llava-mod_b200"))
+from llavamod import kernels as K  # noqa: E402
+
+dev = "cuda"
+REPS = int(os.environ.get("REPS", "1"))
+
+
+def timed(name, fn, work, unit):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / REPS
+    print("%-46s %8.3f ms  %9.1f %s" % (name, ms, work / (ms * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9), unit))
+
+
+def main():
+    T, V = 2048, 151936
+    # teacher gate|up GEMM, student gate|up, wgrad, lm_head
+    for (M, N, Kd, a_mn, b_mn, tag) in [(T, 22016, 4096, False, False, "teacher gate|up fwd"), (T, 5632, 1024, False, False, "student gate|up fwd"),
+                                        (T, 1024, 5632, False, True, "student dgrad (B MN-major)"), (5632, 1024, T, True, True, "student wgrad (A,B MN-major)"),
+                                        (T, V, 1024, False, False, "student lm_head")]:
+        a = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).to(torch.bfloat16)
+        b = torch.randn((Kd, N) if b_mn else (N, Kd), device=dev).to(torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        timed("gemm %s %dx%dx%d" % (tag, M, N, Kd), lambda: K.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=out), 2.0 * M * N * Kd, "TFLOP/s")
+    # grouped expert GEMM on compact rows (4 experts, ~1024 rows each)
+    offs = torch.tensor([0, 1024, 2176, 3072, 4096], dtype=torch.int32, device=dev)
+    xp = torch.randn(4608, 1024, device=dev).to(torch.bfloat16)
+    w = torch.randn(4, 5632, 1024, device=dev).to(torch.bfloat16)
+    h1 = torch.zeros(4608, 5632, device=dev, dtype=torch.bfloat16)
+    timed("grouped expert gemm 4x[~1024,5632,1024]", lambda: K.grouped_gemm(xp, w, h1, offs, 0), 2.0 * 4096 * 5632 * 1024, "TFLOP/s")
+    # attention forward: teacher (32 heads, hd 128), student (16 heads, hd 64), CLIP (non-causal 577)
+    for (B, Tt, nh, hd, causal, tag) in [(1, T, 32, 128, True, "teacher"), (1, T, 16, 64, True, "student"), (1, 577, 16, 64, False, "CLIP")]:
+        qkv = torch.randn(B * Tt, 3 * nh * hd, device=dev).to(torch.bfloat16)
+        fl = 4.0 * B * nh * Tt * Tt * hd * (0.5 if causal else 1.0)
+        timed("attn fwd %s T%d nh%d hd%d" % (tag, Tt, nh, hd), lambda: K.attention_fwd(qkv, B, Tt, nh, nh, hd, causal), fl, "TFLOP/s")
+    # fused KL + CE fwd/bwd, all rows active and the 40%-masked workload
+    s = (torch.randn(T, V, device=dev) * 2).to(torch.bfloat16)
+    t = (torch.randn(T, V, device=dev) * 2).to(torch.bfloat16)
+    for frac, tag in ((0.0, "all rows active"), (0.4, "40% masked (bench workload)")):
+        labels = torch.randint(0, V, (T,), device=dev)
+        labels[: int(frac * T)] = -100
+        active = int(((labels != -100) | torch.cat([labels[1:] != -100, torch.zeros(1, dtype=torch.bool, device=dev)])).sum())
+        by = active * 6 * V + (T - active) * 2 * V
+        d = torch.empty_like(s)
+        timed("kl_fused fwd+bwd [2048,151936] " + tag, lambda: K.kl_fused(s, t, labels, T, V, 1.0, 1.0, False, dlogits=d), by, "GB/s")
+    # router + scatter
+    x = torch.randn(T, 1024, device=dev).to(torch.bfloat16)
+    wg = torch.randn(4, 1024, device=dev) * 0.1
+    noise = torch.randn(T, 4, device=dev)
+    timed("moe_route_scatter S2048 H1024 E4", lambda: K.moe_route_scatter(x, wg, noise, 1.5, 0), T * 3 * 1024 * 2, "GB/s")
+
+
+if __name__ == "__main__":
+    main()
