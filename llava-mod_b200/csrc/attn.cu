@@ -136,7 +136,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
-      mbar_wait_bounded(&s_full[s], (j >> 1) & 1);
+      mbar_wait_warp(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
       uint32_t sv[BKV];
       tmem_ld32(tS0 + s * BKV + lane_off, sv);
@@ -168,7 +168,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       const bool moved = mx > m;
       m = mx;
       if (j > 0) {
-        mbar_wait_bounded(&pv_done, (j - 1) & 1);            // O holds blocks 0..j-1
+        mbar_wait_warp(&pv_done, (j - 1) & 1);               // O holds blocks 0..j-1
         tc_fence_after();
         if (__any_sync(0xffffffffu, moved)) {                // rescale O only when some row of this warp raised its max
 #pragma unroll
@@ -188,7 +188,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       if (lane == 0) mbar_arrive(&p_full[s]);
     }
     // ---- epilogue ----
-    mbar_wait_bounded(&pv_done, (nblk - 1) & 1);
+    mbar_wait_warp(&pv_done, (nblk - 1) & 1);
     tc_fence_after();
     const float inv = (l > 0.f) ? 1.f / l : 0.f;
     const bool ok = qrow < p.T;

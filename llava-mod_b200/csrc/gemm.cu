@@ -13,6 +13,7 @@
 //   mbarriers     : full[stage] (TMA complete_tx) / empty[stage] (tcgen05.commit) / tmem_full[2] / tmem_empty[2]
 // Operand "major-ness" is a template parameter, so dgrad (B = W as stored, MN-major) and wgrad (A = dY^T, B = X^T, both MN-major)
 // run without transposes; the UMMA shared-memory descriptors and the TMA boxes change, the pipeline does not.
+#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace {
@@ -38,6 +39,7 @@ struct GemmParams {
   int bn;                          // tile width (256 or 128)
   int beta;                        // 1: D = bf16(D + acc)
   int splits;                      // split-K factor (>1: fp32 atomic accumulation into D32)
+  int dbg_nostore;                 // timing experiments only (LMOD_GEMM_NOSTORE=1): epilogue drains TMEM but does not write D
   // grouped (experts): row ranges from `offsets` (device), B / D32 advance per group
   const int32_t* offsets;          // [groups+1] or null
   int groups;
@@ -186,7 +188,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     Tile t;
     for (int ti = blockIdx.x; get_tile(p, ti, t); ti += gridDim.x, ++it) {
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-      mbar_wait_bounded(&tmem_full[acc], acc_phase);
+      mbar_wait_warp(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = t.m0 + q * 32 + lane;
       const bool row_ok = row < t.m_end;
@@ -198,7 +200,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         uint32_t r[32];
         tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
         const int col0 = t.n0 + c * 32;
-        if (!row_ok || col0 >= p.N) continue;
+        if (!row_ok || col0 >= p.N || p.dbg_nostore) continue;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const int col = col0 + v * 8;
@@ -240,6 +242,198 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// =================================================================================================================================
+// 2-CTA variant (cta_group::2): a CTA PAIR (cluster of 2, same TPC) owns a 256 x 256 output tile.  Each CTA stages its own 128 rows
+// of A and only HALF of B (128 of the 256 columns) -- the UMMA reads B from both CTAs' shared memory -- so shared-memory and L2
+// traffic per FLOP halve.  The leader CTA (rank 0) issues tcgen05.mma.cta_group::2 (M = 256); both CTAs run a TMA producer (their
+// loads complete_tx on the LEADER's full barrier) and an epilogue over their own 128 TMEM lanes.  tcgen05.commit multicasts the
+// "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely on the leader's tmem_empty.
+constexpr int STAGES2 = 6;
+constexpr int B2_STAGE_BYTES = 128 * BK * 2;                    // half of the 256-wide B tile per CTA
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;    // 32 KB
+constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + 1024;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                     // clears the CTA-pair rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(leader_bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {       // arrive on the same-offset barrier of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {     // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES2], empty_bar[STAGES2], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int num_m = (p.M + 255) / 256, num_n = (p.N + 255) / 256, num_k = (p.K + BK - 1) / BK;
+  const int ntiles = num_m * num_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }     // 4 epilogue warps x 2 CTAs (leader's copy)
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_b) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // both CTAs' barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer (both CTAs: own half of A rows and of B rows) =====================
+    uint32_t stage = 0, phase = 0;
+    for (int t = cluster; t < ntiles; t += nclusters) {
+      const int m0 = (t % num_m) * 256 + 128 * (int)rank, n0 = (t / num_m) * 256 + 128 * (int)rank;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE2_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);          // bytes of BOTH CTAs land on the leader's barrier
+        if (!A_MN) {
+          tma_load_2d_2sm(sa, &tma_a, kb * BK, m0, &full_bar[stage]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sa + j * (BK * 128), &tma_a, m0 + 64 * j, kb * BK, &full_bar[stage]);
+        }
+        if (!B_MN) {
+          tma_load_2d_2sm(sb, &tma_b, kb * BK, n0, &full_bar[stage]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sb + j * (BK * 128), &tma_b, n0 + 64 * j, kb * BK, &full_bar[stage]);
+        }
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(256 >> 3) << 17) |
+                           ((uint32_t)(256 >> 4) << 24);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int t = cluster; t < ntiles; t += nclusters, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      uint32_t first = 1;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait_bounded(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES), sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma2_f16(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        umma2_commit_mc(&empty_bar[stage]);
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+      }
+      umma2_commit_mc(&tmem_full[acc]);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int t = cluster; t < ntiles; t += nclusters, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      mbar_wait_warp(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = (t % num_m) * 256 + 128 * (int)rank + q * 32 + lane;
+      const int n00 = (t / num_m) * 256;
+      const bool row_ok = row < p.M;
+      __nv_bfloat16* drow = p.D ? p.D + (int64_t)row * p.ldd : nullptr;
+      float* d32row = p.D32 ? p.D32 + (int64_t)row * p.ldd : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
+        const int col0 = n00 + c * 32;
+        if (!row_ok || col0 >= p.N || p.dbg_nostore) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int col = col0 + v * 8;
+          if (col >= p.N) break;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
+          if (p.bias) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+            f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
+            f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
+          }
+          if (d32row) {
+            float4* o = reinterpret_cast<float4*>(d32row + col);
+            float4 a = o[0], b2 = o[1];
+            a.x += f[0]; a.y += f[1]; a.z += f[2]; a.w += f[3]; b2.x += f[4]; b2.y += f[5]; b2.z += f[6]; b2.w += f[7];
+            o[0] = a; o[1] = b2;
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(drow + col);
+            if (p.beta) {
+              const uint4 old = *o;
+              f[0] += bf16lo(old.x); f[1] += bf16hi(old.x); f[2] += bf16lo(old.y); f[3] += bf16hi(old.y);
+              f[4] += bf16lo(old.z); f[5] += bf16hi(old.z); f[6] += bf16lo(old.w); f[7] += bf16hi(old.w);
+            }
+            uint4 w;
+            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+            *o = w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // the pair frees its tensor memory together
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    LMOD_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
+    attr = true;
+  }
+  const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  int clusters = lmod_num_sms() / 2;
+  if (tiles < clusters) clusters = tiles;
+  gemm2_tcgen05_kernel<A_MN, B_MN><<<2 * clusters, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, p);
+  LMOD_LAUNCH_OK();
+  return LMOD_OK;
+}
+int dispatch2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2<false, false>(ta, tb, p, st);
+  if (!a_mn && b_mn) return launch2<false, true>(ta, tb, p, st);
+  if (a_mn && b_mn) return launch2<true, true>(ta, tb, p, st);
+  return launch2<true, false>(ta, tb, p, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -287,6 +481,22 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   CUtensorMap ta, tb;
   int rc;
   const int splits_req = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
+  static const int two_cta_env = getenv("LMOD_GEMM_2CTA") ? atoi(getenv("LMOD_GEMM_2CTA")) : 1;
+  const int64_t tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
+  if (two_cta_env && splits_req == 1 && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2) {
+    // CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 rows of A and 128 rows of B
+    if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 128);
+    else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+    if (rc) return rc;
+    if (!b_mn_major) rc = make_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 128);
+    else rc = make_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+    if (rc) return rc;
+    GemmParams p2 = {};
+    p2.D = (__nv_bfloat16*)D; p2.bias = (const __nv_bfloat16*)bias; p2.D32 = d_f32_accum; p2.ldd = ldd;
+    p2.M = (int)M; p2.N = (int)N; p2.K = (int)K; p2.beta = epilogue & 1; p2.splits = 1; p2.groups = 1; p2.bn = 256;
+    p2.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
+    return dispatch2(a_mn_major != 0, b_mn_major != 0, ta, tb, p2, (cudaStream_t)stream);
+  }
   const int BN = pick_bn(((M + BM - 1) / BM) * splits_req, N);
   if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
   else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
@@ -297,6 +507,7 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   GemmParams p = {};
   p.D = (__nv_bfloat16*)D; p.bias = (const __nv_bfloat16*)bias; p.D32 = d_f32_accum; p.ldd = ldd;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.beta = epilogue & 1; p.offsets = nullptr; p.groups = 1; p.bn = BN;
+  p.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
   p.splits = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
   LMOD_CHECK_ARG(p.splits == 1 || d_f32_accum, "lmod_gemm_bf16: split-K needs the fp32 accumulate output");
   const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN)) * p.splits;

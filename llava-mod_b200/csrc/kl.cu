@@ -14,11 +14,11 @@
 //   * two CTAs are resident per SM (<= 2 x 76 KB smem) so one CTA's loads overlap the other's math.
 //   * rows whose KD mask and CE mask are both 0 contribute nothing (reference multiplies by 0):
 //     their loads are skipped and their gradient slice is zero-filled.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr int KL_THREADS = 256;
 constexpr int KL_CHUNKS = 4;       // mbarrier-tracked load chunks per slice
 constexpr int KL_MAX_CS = 8;
 
@@ -66,6 +66,7 @@ __device__ __forceinline__ void accum_pair(uint32_t sw, uint32_t tw, float nms, 
   a = fmaf(et1, s1, a);
 }
 
+template <int KL_THREADS>
 __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(16) Xchg xchg[2];
@@ -326,6 +327,33 @@ extern "C" int lmod_kl_finalize(const float* row_out, const int64_t* labels, int
   return LMOD_OK;
 }
 
+template <int T>
+int kl_launch(KlParams p, int cs, size_t smem, int64_t n_rows, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    LMOD_CUDA_OK(cudaFuncSetAttribute(kl_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(cs);
+  static int cached_clusters[2] = {0, 0};        // per cluster size (1 / 8): queried once, outside any stream capture
+  int& max_clusters = cached_clusters[cs == 1 ? 0 : 1];
+  if (max_clusters <= 0) {
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_fused_kernel<T>, &cfg);
+    if (e != cudaSuccess || max_clusters <= 0) { (void)cudaGetLastError(); max_clusters = lmod_num_sms() / cs; }
+  }
+  int64_t ncl = n_rows < max_clusters ? n_rows : max_clusters;
+  cfg.gridDim = dim3((unsigned)(ncl * cs));
+  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_fused_kernel<T>, p));
+  lmod_count_launch();
+  return LMOD_OK;
+}
+
 extern "C" int lmod_kl_fwd_bwd(const void* s_logits, int64_t ld_s, const void* t_logits, int64_t ld_t,
                                const int64_t* labels, int64_t n_rows, int64_t seq_len, int64_t vocab,
                                int distill_all, float w_kd, float w_ce, const float* counts2,
@@ -343,33 +371,12 @@ extern "C" int lmod_kl_fwd_bwd(const void* s_logits, int64_t ld_s, const void* t
   size_t smem = (size_t)slice * 2 * 2;
   LMOD_CHECK_ARG(smem <= 220 * 1024, "lmod_kl_fwd_bwd: vocab %lld too large for the 8-CTA cluster layout", (long long)vocab);
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(kl_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_done = true;
-  }
   KlParams p;
   p.s = (const __nv_bfloat16*)s_logits; p.t = (const __nv_bfloat16*)t_logits; p.labels = labels;
   p.counts = counts2; p.row_out = row_out; p.d = (__nv_bfloat16*)dlogits;
   p.ld_s = ld_s; p.ld_t = ld_t; p.ld_d = ld_d; p.n_rows = n_rows; p.seq_len = seq_len;
   p.vocab = (int)vocab; p.slice = slice; p.distill_all = distill_all; p.w_kd = w_kd; p.w_ce = w_ce;
 
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(KL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cfg.gridDim = dim3(cs);
-  static int cached_clusters[2] = {0, 0};        // per cluster size (1 / 8): queried once, outside any stream capture
-  int& max_clusters = cached_clusters[cs == 1 ? 0 : 1];
-  if (max_clusters <= 0) {
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_fused_kernel, &cfg);
-    if (e != cudaSuccess || max_clusters <= 0) { (void)cudaGetLastError(); max_clusters = lmod_num_sms() / cs; }
-  }
-  int64_t ncl = n_rows < max_clusters ? n_rows : max_clusters;
-  cfg.gridDim = dim3((unsigned)(ncl * cs));
-  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_fused_kernel, p));
-  lmod_count_launch();
-  return LMOD_OK;
+  static const int kl_threads = getenv("LMOD_KL_THREADS") ? atoi(getenv("LMOD_KL_THREADS")) : 256;   // measured: 256 thr x 109 regs = 0.67 ms, 512 thr x 64 regs = 0.88 ms (all rows active)
+  return (kl_threads == 256) ? kl_launch<256>(p, cs, smem, n_rows, (cudaStream_t)stream) : kl_launch<512>(p, cs, smem, n_rows, (cudaStream_t)stream);
 }

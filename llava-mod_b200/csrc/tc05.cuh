@@ -12,6 +12,12 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t phase)
     if (++spins > (1u << 26)) { printf("lmod tcgen05 kernel: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
+// whole-warp wait: one lane polls the barrier, the other 31 sleep at the warp barrier (polling threads cost issue slots and power --
+// the GEMM is power-capped on B200, so idle threads must really be idle)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t phase) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_bounded(bar, phase);
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");

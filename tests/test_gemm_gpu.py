@@ -34,6 +34,26 @@ def test_gemm_all_layouts(M, N, K, a_mn, b_mn):
     check(out, ref_mm(a, b, a_mn, b_mn), K)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(2048, 4096, 512), (1900, 3904, 520)])
+def test_gemm_two_cta_path(M, N, K, a_mn, b_mn):
+    """Problems with >= 111 256x256 tiles run on the CTA-pair (cta_group::2) kernel."""
+    from llavamod import kernels as Kk
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    pad = lambda n: (n + 7) // 8 * 8          # noqa: E731
+    a = torch.randn((K, pad(M)) if a_mn else (M, pad(K)), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((K, pad(N)) if b_mn else (N, pad(K)), device="cuda", generator=g).to(torch.bfloat16)
+    a = a[:, :M] if a_mn else a[:, :K]
+    b = b[:, :N] if b_mn else b[:, :K]
+    bias = torch.randn(N, device="cuda", generator=g).to(torch.bfloat16)
+    out = Kk.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias)
+    torch.cuda.synchronize()
+    check(out, ref_mm(a, b, a_mn, b_mn) + bias.float(), K)
+    acc = torch.zeros(M, N, device="cuda")
+    Kk.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_f32=acc)
+    torch.testing.assert_close(acc, ref_mm(a, b, a_mn, b_mn), rtol=1e-4, atol=2e-2)
+
+
 def test_gemm_bias_beta_and_f32_accumulate():
     from llavamod import kernels as Kk
     M, N, K = 384, 768, 320
