@@ -178,6 +178,11 @@ int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ld
  * lse [batch, nh, seq] fp32 (natural-log LSE of the scaled scores -- what flash-attn's backward consumes) or NULL. */
 int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
                   float softmax_scale, void* out, int64_t ld_o, float* lse, void* stream);
+/* flash-attention BACKWARD on tcgen05 (autograd of the call above): dqkv (fused dq|dk|dv, same layout as qkv) from qkv, out, dout, lse.
+ * dq32_ws: fp32 [batch*seq, nh*hd] workspace (zeroed inside), dsum_ws: fp32 [batch, nh, seq] workspace. */
+int lmod_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_o, const void* dout, int64_t ld_do,
+                  const float* lse, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal, float softmax_scale,
+                  void* dqkv, int64_t ld_dqkv, float* dq32_ws, float* dsum_ws, void* stream);
 
 
 #ifdef __cplusplus

@@ -9,7 +9,7 @@ namespace {
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t phase) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, phase)) {
-    if (++spins > (1u << 26)) { printf("lmod tcgen05 kernel: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (++spins > (1u << 22)) { printf("lmod tcgen05 kernel: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
 // whole-warp wait: one lane polls the barrier, the other 31 sleep at the warp barrier (polling threads cost issue slots and power --

@@ -130,7 +130,10 @@ def linear(x, w, bias=None, wgrad=None, bgrad=None):
 # ---------------------------------------------------------------------------------------------------
 # attention (K7)
 # ---------------------------------------------------------------------------------------------------
+import os as _os
+
 ATTN_HEAD_DIMS = (64, 128)
+ATTN_BWD_TCGEN05 = _os.environ.get("LLAVAMOD_ATTN_BWD", "flash") == "tcgen05"
 
 
 def attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale=None, need_lse=False):
@@ -144,8 +147,8 @@ def attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale=None, need_lse=False):
 
 
 class AttnFn(Function):
-    """Qwen2SdpaAttention core (modeling_qwen2.py:713-721).  Forward: our tcgen05 kernel.  Backward (student only): flash-attn 2's
-    library backward fed with our output and log-sum-exp, writing dq|dk|dv straight into one fused gradient buffer."""
+    """Qwen2SdpaAttention core (modeling_qwen2.py:713-721): our tcgen05 forward (lmod_attn_fwd); backward = flash-attn 2 library kernel
+    by default, our tcgen05 backward (lmod_attn_bwd) with LLAVAMOD_ATTN_BWD=tcgen05.  dq|dk|dv come back as one fused buffer."""
 
     @staticmethod
     def forward(ctx, qkv, B, T, nh, nkv, hd, causal, scale):
@@ -157,9 +160,13 @@ class AttnFn(Function):
 
     @staticmethod
     def backward(ctx, dout):
-        from flash_attn.flash_attn_interface import _wrapped_flash_attn_backward
         qkv, out, lse = ctx.saved_tensors
         B, T, nh, nkv, hd, causal, scale = ctx.dims
+        if ATTN_BWD_TCGEN05:
+            return attention_bwd(qkv, out, _c(dout), lse, B, T, nh, nkv, hd, causal, scale), None, None, None, None, None, None, None
+        # default this round: flash-attn 2's library backward, fed with OUR forward's output and log-sum-exp and writing dq|dk|dv
+        # straight into one fused buffer (our tcgen05 backward is parity-green but 1.5-2.6x slower)
+        from flash_attn.flash_attn_interface import _wrapped_flash_attn_backward
         q = qkv[:, : nh * hd].view(B, T, nh, hd)
         k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)
         v = qkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd)
@@ -170,6 +177,16 @@ class AttnFn(Function):
         _wrapped_flash_attn_backward(_c(dout).view(B, T, nh, hd), q, k, v, out.view(B, T, nh, hd), lse, dq, dk, dv, 0.0, scale, bool(causal),
                                      -1, -1, 0.0, None, False, rng_state=None)
         return dqkv, None, None, None, None, None, None, None
+
+
+def attention_bwd(qkv, out, dout, lse, B, T, nh, nkv, hd, causal, scale):
+    """Hand-written tcgen05 flash-attention backward -> fused dqkv (same layout as qkv)."""
+    dqkv = torch.empty_like(qkv)
+    dq32 = torch.empty(B * T, nh * hd, dtype=torch.float32, device=qkv.device)
+    dsum = torch.empty(B, nh, T, dtype=torch.float32, device=qkv.device)
+    call("lmod_attn_bwd", ptr(qkv), qkv.stride(0), ptr(out), out.stride(0), ptr(dout), dout.stride(0), ptr(lse), B, T, nh, nkv, hd,
+         1 if causal else 0, float(scale), ptr(dqkv), dqkv.stride(0), ptr(dq32), ptr(dsum))
+    return dqkv
 
 
 # ---------------------------------------------------------------------------------------------------

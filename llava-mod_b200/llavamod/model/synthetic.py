@@ -16,13 +16,14 @@ ARCH = {
                          num_key_value_heads=16, vocab_size=151936, rope_theta=1e6, tie_word_embeddings=False),
     "qwen1.5-7b": dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
                        num_key_value_heads=32, vocab_size=151936, rope_theta=1e6, tie_word_embeddings=False),
-    "tiny": dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
-                 num_key_value_heads=4, vocab_size=512, rope_theta=1e6, tie_word_embeddings=False),
+    # config 1 of BASELINE.json (2-layer / 128-d); 2 heads -> head_dim 64, so the tcgen05 attention kernel is the one that runs
+    "tiny": dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                 num_key_value_heads=2, vocab_size=512, rope_theta=1e6, tie_word_embeddings=False),
 }
 CLIP = {
     "clip-l-336": dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
                        image_size=336, patch_size=14),
-    "tiny": dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, image_size=32, patch_size=8),
+    "tiny": dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=1, image_size=32, patch_size=8),
 }
 
 TRAIN_MODULES = ["mlp.gate_proj", "mlp.up_proj", "mlp.down_proj", "wg"]      # dense2sparse_distillation.sh

@@ -23,6 +23,9 @@ CASES = {
                       B=2, T=20, img_pos=[[3], [7]], pad=[0, 3]),
     "dense_gqa": dict(kw=dict(hidden=128, inter=192, layers=2, heads=4, kv_heads=2, vocab=384, seed=1),
                       B=3, T=24, img_pos=[[2, 11], [], [0]], pad=[0, 5, 9]),
+    # head_dim 64 (2 heads x 64, CLIP 1 head x 64): the shapes our tcgen05 attention kernel is built for
+    "dense_hd64": dict(kw=dict(hidden=128, inter=256, layers=2, heads=2, kv_heads=1, vocab=512, seed=3, clip_heads=1),
+                       B=2, T=30, img_pos=[[4], [9]], pad=[0, 0]),
     "dense_nopad": dict(kw=dict(hidden=128, inter=256, layers=2, heads=4, kv_heads=4, vocab=512, seed=2),
                         B=2, T=16, img_pos=[[5], [5]], pad=[0, 0]),
 }

@@ -67,7 +67,7 @@ def test_checkpoint_key_layout_equals_reference(name, golden_dir):
     from llavamod.model import LlavaQwen1_5Config, LlavaQwen1_5ForCausalLM
     fx = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
     kw = fx["kw"]
-    clip = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, image_size=32, patch_size=8)
+    clip = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=kw.get("clip_heads", 4), image_size=32, patch_size=8)
     cfg = LlavaQwen1_5Config(vocab_size=kw["vocab"], hidden_size=kw["hidden"], intermediate_size=kw["inter"],
                              num_hidden_layers=kw["layers"], num_attention_heads=kw["heads"], num_key_value_heads=kw["kv_heads"],
                              rope_theta=1e6, mm_image_tower=clip, image_projector_type="mlp2x_gelu", mm_hidden_size=64,

@@ -13,11 +13,11 @@ import torch
 from oracle import restated as R
 from oracle import ref_shim
 
-CASES = ["dense_mha", "dense_gqa", "dense_nopad"]
+CASES = ["dense_mha", "dense_gqa", "dense_nopad", "dense_hd64"]
 
 
 def cfgs_from_kw(kw):
-    cc = R.ClipCfg(hidden=64, inter=128, layers=3, heads=4, image=32, patch=8)
+    cc = R.ClipCfg(hidden=64, inter=128, layers=3, heads=kw.get("clip_heads", 4), image=32, patch=8)
     lc = R.LMCfg(hidden=kw["hidden"], inter=kw["inter"], layers=kw["layers"], heads=kw["heads"],
                  kv_heads=kw["kv_heads"], vocab=kw["vocab"], kd_vocab=kw["vocab"])
     return cc, lc
