@@ -161,6 +161,8 @@ int lmod_adamw(float* master, float* m, float* v, const void* grad, int grad_is_
  *   a_mn_major / b_mn_major: 0 = operand stored K-major ([rows,K], "T"), 1 = stored MN-major ([K,rows], "N"), so that
  *   dgrad (B = W as stored) and wgrad (A = dY^T, B = X^T) need no transposed copies.
  *   epilogue bit0: D = bf16(D + acc).  bias [N] optional.  d_f32_accum != NULL: fp32 D32[M,ldd] += acc instead of D.
+ *   epilogue bit1: fused SwiGLU -- B's rows are tile-interleaved [128 gate rows | 128 up rows] per 256 and D[M, N/2] =
+ *   bf16(bf16(silu(g)) * u) (modeling_qwen2.py:199-200); only where lmod_gemm_swiglu_ok(M, N) says so.  bits 8..: split-K factor.
  * Grouped form = DeepSpeed Experts.forward on COMPACT rows (offsets from lmod_moe_route_scatter, 128-row aligned):
  *   mode 0 fwd  : D[rows_g,N] = A[rows_g,K] * B[g][N,K]^T     mode 1 dgrad: D[rows_g,N] = A[rows_g,K] * B[g][K,N]
  *   mode 2 wgrad: D[g][M,N] (+)= A[rows_g,M]^T * B[rows_g,N]
@@ -168,6 +170,7 @@ int lmod_adamw(float* master, float* m, float* v, const void* grad, int grad_is_
 int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, const void* bias, int epilogue,
                    float* d_f32_accum, void* stream);
+int lmod_gemm_swiglu_ok(int64_t M, int64_t N);
 int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
                            const int32_t* offsets, int G, int64_t max_rows, int64_t M, int64_t N, int64_t K,
                            int mode, int epilogue, void* stream);

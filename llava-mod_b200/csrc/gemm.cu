@@ -39,6 +39,7 @@ struct GemmParams {
   int bn;                          // tile width (256 or 128)
   int beta;                        // 1: D = bf16(D + acc)
   int splits;                      // split-K factor (>1: fp32 atomic accumulation into D32)
+  int swiglu;                      // CTA-pair kernel only: tile = [128 gate | 128 up] columns -> D[:, N/2] = bf16(bf16(silu(g)) * u)
   int dbg_nostore;                 // timing experiments only (LMOD_GEMM_NOSTORE=1): epilogue drains TMEM but does not write D
   // grouped (experts): row ranges from `offsets` (device), B / D32 advance per group
   const int32_t* offsets;          // [groups+1] or null
@@ -368,6 +369,34 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const bool row_ok = row < p.M;
       __nv_bfloat16* drow = p.D ? p.D + (int64_t)row * p.ldd : nullptr;
       float* d32row = p.D32 ? p.D32 + (int64_t)row * p.ldd : nullptr;
+      if (p.swiglu) {
+        // fused SwiGLU epilogue (Qwen2MLP act_fn(gate_proj(x)) * up_proj(x), modeling_qwen2.py:199-200): the weight rows of this
+        // 256-wide tile are [128 gate rows | 128 matching up rows], so gate and up of the same output column sit in this thread's lane
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), g);
+          tmem_ld32(tmem_base + acc * 256 + 128 + c * 32 + ((uint32_t)(q * 32) << 16), u);
+          const int col0 = (n00 >> 1) + c * 32;
+          if (!row_ok || col0 >= (p.N >> 1)) continue;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float gb = bf16_round(__uint_as_float(g[v * 8 + j])), ub = bf16_round(__uint_as_float(u[v * 8 + j]));   // reference rounds both GEMM outputs to bf16
+              f[j] = bf16_round(gb * (1.f / (1.f + __expf(-gb)))) * ub;      // same expression as silu_mul_fwd_kernel -> bit-identical
+            }
+            uint4 w;
+            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(drow + col0 + v * 8) = w;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
@@ -472,6 +501,7 @@ int pick_bn(int64_t m_tiles, int64_t N) {
 
 // D[M,N] = A * B^T.  a_mn_major = 0: A stored [M,K] (row stride lda) ; 1: A stored [K,M].  b_mn_major = 0: B stored [N,K] ; 1: B stored [K,N].
 // epilogue bit 0: D = bf16(D + acc) ;  d_f32_accum != null: fp32 D32 += acc (ldd applies to it) instead of the bf16 output;
+// epilogue bit 1: fused SwiGLU (B rows tile-interleaved [128 gate | 128 up] per 256; D has N/2 columns; CTA-pair kernel only);
 // epilogue bits 8..: split-K factor (fp32 atomic accumulation into D32, which the caller zero-initialises).
 extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
                               int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum, void* stream) {
@@ -483,7 +513,10 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   const int splits_req = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
   static const int two_cta_env = getenv("LMOD_GEMM_2CTA") ? atoi(getenv("LMOD_GEMM_2CTA")) : 1;
   const int64_t tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
-  if (two_cta_env && splits_req == 1 && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2) {
+  const bool pair = two_cta_env && splits_req == 1 && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2;
+  if (epilogue & 2) LMOD_CHECK_ARG(pair && N % 256 == 0 && D && !d_f32_accum && !bias && !(epilogue & 1),
+                                   "lmod_gemm_bf16: the SwiGLU epilogue needs the CTA-pair kernel (>= 111 256x256 tiles) and N %% 256 == 0");
+  if (pair) {
     // CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 rows of A and 128 rows of B
     if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 128);
     else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
@@ -495,6 +528,7 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
     p2.D = (__nv_bfloat16*)D; p2.bias = (const __nv_bfloat16*)bias; p2.D32 = d_f32_accum; p2.ldd = ldd;
     p2.M = (int)M; p2.N = (int)N; p2.K = (int)K; p2.beta = epilogue & 1; p2.splits = 1; p2.groups = 1; p2.bn = 256;
     p2.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
+    p2.swiglu = (epilogue & 2) ? 1 : 0;
     return dispatch2(a_mn_major != 0, b_mn_major != 0, ta, tb, p2, (cudaStream_t)stream);
   }
   const int BN = pick_bn(((M + BM - 1) / BM) * splits_req, N);
@@ -512,6 +546,13 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   LMOD_CHECK_ARG(p.splits == 1 || d_f32_accum, "lmod_gemm_bf16: split-K needs the fp32 accumulate output");
   const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN)) * p.splits;
   return dispatch(a_mn_major != 0, b_mn_major != 0, ta, tb, p, tiles, (cudaStream_t)stream);
+}
+
+// 1 when lmod_gemm_bf16 would run this problem on the CTA-pair kernel (which is the one that offers the fused SwiGLU epilogue)
+extern "C" int lmod_gemm_swiglu_ok(int64_t M, int64_t N) {
+  static const int two_cta_env = getenv("LMOD_GEMM_2CTA") ? atoi(getenv("LMOD_GEMM_2CTA")) : 1;
+  const int64_t tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
+  return (two_cta_env && N % 256 == 0 && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2) ? 1 : 0;
 }
 
 // Grouped (per-expert) GEMM on rows [offsets[g], offsets[g+1]) (device array; boundaries must be multiples of 128 for mode 0/1, of 64 for

@@ -78,6 +78,31 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, ou
     return out
 
 
+_swiglu_cache = {}
+
+
+def swiglu_mlp_in(x, w_gu):
+    """Frozen-weight fast path of act_fn(gate_proj(x)) * up_proj(x): ONE GEMM whose epilogue applies SwiGLU, so the [rows, 2I] gate|up
+    activation is never written.  The kernel wants the fused weight tile-interleaved ([128 gate rows | 128 up rows] per 256); that copy is
+    built once per (frozen) weight.  Returns None when the shape does not qualify (caller falls back to GEMM + silu_mul)."""
+    x2 = _rows(x)
+    M = x2.shape[0]
+    N, H = w_gu.shape
+    I = N // 2
+    if w_gu.requires_grad or I % 128 != 0 or not _C.lib().lmod_gemm_swiglu_ok(M, N):
+        return None
+    key = (w_gu.data_ptr(), w_gu._version)
+    ent = _swiglu_cache.get(w_gu.data_ptr())
+    if ent is None or ent[0] != key:
+        g = w_gu[:I].view(I // 128, 128, H)
+        u = w_gu[I:].view(I // 128, 128, H)
+        ent = (key, torch.stack([g, u], 1).reshape(N, H).contiguous())
+        _swiglu_cache[w_gu.data_ptr()] = ent
+    out = torch.empty(M, I, dtype=x.dtype, device=x.device)
+    call("lmod_gemm_bf16", ptr(x2), x2.stride(0), 0, ptr(ent[1]), H, 0, ptr(out), I, M, N, H, None, 2, None)
+    return out
+
+
 def grouped_gemm(a, b, out, offsets, mode, max_rows=None, accumulate=False):
     """lmod_grouped_gemm_bf16 on compact expert rows (offsets [G+1] int32 on device, 128-aligned).
        mode 0: out[R,N] = a[R,K] @ b[G,N,K]^T ; mode 1: out[R,N] = a[R,K] @ b[G,K,N] ; mode 2: out[G,M,N] (+)= a[R,M]^T @ b[R,N] per group."""

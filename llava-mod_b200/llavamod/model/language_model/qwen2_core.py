@@ -305,8 +305,12 @@ class Qwen2Model(nn.Module):
                 l_auxes.append(l_aux)
                 branch = None
             else:
-                gu = K.linear(x, mlp.gu_weight, None, self.gview(mlp.gu_weight), None)
-                act = K.silu_mul(gu)
+                act = None
+                if not torch.is_grad_enabled() or not (x.requires_grad or mlp.gate_proj.weight.requires_grad):
+                    act = K.swiglu_mlp_in(x, mlp.gu_weight)                  # frozen teacher: SwiGLU fused into the GEMM epilogue
+                if act is None:
+                    gu = K.linear(x, mlp.gu_weight, None, self.gview(mlp.gu_weight), None)
+                    act = K.silu_mul(gu)
                 branch = K.linear(act, mlp.down_proj.weight, None, self.gview(mlp.down_proj.weight), None)
         if branch is None:
             out, _ = K.rmsnorm(stream, self.norm.weight, cfg.rms_norm_eps)

@@ -54,6 +54,23 @@ def test_gemm_two_cta_path(M, N, K, a_mn, b_mn):
     torch.testing.assert_close(acc, ref_mm(a, b, a_mn, b_mn), rtol=1e-4, atol=2e-2)
 
 
+def test_gemm_fused_swiglu_epilogue():
+    """One GEMM + fused SwiGLU == GEMM then silu_mul kernel (bit exact: same bf16 roundings), and close to the fp32 formula."""
+    from llavamod import kernels as Kk
+    M, H, I = 2048, 512, 2816 + 128 * 10          # I % 128 == 0, enough 256x256 tiles for the CTA-pair kernel
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(M, H, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(2 * I, H, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    fused = Kk.swiglu_mlp_in(x, w)
+    assert fused is not None
+    two_step = Kk.silu_mul(Kk.gemm(x, w))
+    assert torch.equal(fused, two_step)
+    ref = torch.nn.functional.silu(x.float() @ w[:I].float().t()) * (x.float() @ w[I:].float().t())
+    # vs the un-rounded fp32 formula: gate, up and silu(gate) are each rounded to bf16 on the way (as in the reference's bf16 modules)
+    err = (fused.float() - ref).abs()
+    assert bool((err <= 2.0 ** -6 * ref.abs() + 0.05).all()), err.max().item()
+
+
 def test_gemm_bias_beta_and_f32_accumulate():
     from llavamod import kernels as Kk
     M, N, K = 384, 768, 320
