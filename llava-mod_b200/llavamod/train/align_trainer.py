@@ -77,6 +77,9 @@ class AlignTrainer(BaseTrainer):
             p.requires_grad = False
         self.share_tower = same_frozen_tower(self.model, self.ref_model.module)
         self.kd_vocab = KD_VOCAB_SIZE
+        import os
+        self.overlap_teacher = bool(int(os.environ.get("LLAVAMOD_OVERLAP_TEACHER", "1"))) and next(model.parameters()).is_cuda
+        self._teacher_stream = torch.cuda.Stream() if self.overlap_teacher else None
 
     # ---- API-compat pieces (materialising forms, our kernels) ------------------------------------------------
     def _moe_loss_of(self, outputs):
@@ -126,10 +129,22 @@ class AlignTrainer(BaseTrainer):
             if plan is None and images is not None and model.get_image_tower() is not None and \
                     model.get_image_tower().num_patches == ref.get_image_tower().num_patches:
                 plan = model.make_splice_plan(fwd["input_ids"], fwd["attention_mask"], fwd["labels"])     # one host plan for both models
+        # The frozen teacher forward and the student forward are independent until the loss: fork the teacher onto a side stream so
+        # the student's small kernels (H=1024: launch/tail bound) fill the gaps of the teacher's machine-filling GEMMs.  Inside a
+        # CUDA-graph capture this becomes a fork/join in the graph.
+        main = torch.cuda.current_stream()
+        side = self._teacher_stream if self.overlap_teacher else None
+        if side is not None:
+            side.wait_stream(main)
+        with torch.no_grad(), torch.cuda.stream(side if side is not None else main):
             t = ref.forward_hidden(**fwd, tower_features=tower_feats, plan=plan)
             th = t["hidden"]
             t_logits = K.mm_nt(th.reshape(-1, th.shape[-1]), ref.lm_head.weight)              # teacher logits, bf16 [N, Vt]
         s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"), plan=plan)
+        if side is not None:
+            main.wait_stream(side)
+            t_logits.record_stream(main)
+            th.record_stream(main)
         labels = s["labels"]
         if s["hidden"].shape[:2] != labels.shape or th.shape[:2] != labels.shape:
             raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
