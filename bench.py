@@ -279,7 +279,7 @@ def run_ours(args):
         last = None
         for _ in range(n_steps):
             for _ in range(accum):
-                last = trainer.training_step(student, batches[it % nb])
+                last = trainer.training_step(student, batches[it % nb], batches[(it + 1) % nb])      # look-ahead: teacher runs one batch ahead
                 it += 1
             if read_loss:
                 _ = float(last)           # D2H read of the step's loss
@@ -376,7 +376,8 @@ def run_ours(args):
                    "gemm": "hand-written tcgen05+TMA GEMM / grouped expert GEMM and tcgen05 flash-attention forward (liblmod_b200); flash-attn 2 library only for the student attention BACKWARD; every other op liblmod_b200",
                    "cuda_graphs": bool(trainer.use_cuda_graphs)},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": accum * (img_bytes + plan_bytes), "d2h_bytes_per_step": 4,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": 2 * accum * (img_bytes + plan_bytes), "d2h_bytes_per_step": 4,
+                "note": "each micro-batch uploads its own inputs and the look-ahead inputs of the next one (teacher runs one batch ahead)",
                 "ms_per_step": ms_e2e / args.steps},
         "roofline": {"kernel": "kl_fused_kernel (lmod_kl_fwd_bwd)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (ach / hbm_peak) if ach else None, "peak_source": src, "traffic": prof.get("traffic_bytes_per_launch"),

@@ -80,6 +80,7 @@ class AlignTrainer(BaseTrainer):
         import os
         self.overlap_teacher = bool(int(os.environ.get("LLAVAMOD_OVERLAP_TEACHER", "1"))) and next(model.parameters()).is_cuda
         self._teacher_stream = torch.cuda.Stream() if self.overlap_teacher else None
+        self.pipeline_teacher = bool(int(os.environ.get("LLAVAMOD_PIPELINE_TEACHER", "1")))
 
     # ---- API-compat pieces (materialising forms, our kernels) ------------------------------------------------
     def _moe_loss_of(self, outputs):
@@ -113,40 +114,58 @@ class AlignTrainer(BaseTrainer):
         return K.align_loss_dense(policy_logprobs, reference_probs, labels, bool(getattr(self.args, "distill_all_tokens", False)))
 
     # ---- the hot loop body ---------------------------------------------------------------------------------------
+    def _device_images(self, model, images):
+        dev = model.device
+        return torch.stack([im.to(dev, non_blocking=True) for im in images]) if not torch.is_tensor(images) else images.to(dev)
+
+    def _teacher_forward(self, fwd, tower_feats, plan):
+        """Frozen teacher -> bf16 logits [N, Vt] (get_p's forward, align_trainer.py:458-461; its softmax lives in the fused kernel)."""
+        ref = self.ref_model.module
+        t = ref.forward_hidden(**fwd, tower_features=tower_feats, plan=plan)
+        th = t["hidden"]
+        return K.mm_nt(th.reshape(-1, th.shape[-1]), ref.lm_head.weight), th.shape[:2]
+
     def compute_loss(self, model, inputs: Dict[str, Union[torch.Tensor, Any]], return_outputs=False):
         assert self.ref_model is not None, "ref model can not be none!"
         ref = self.ref_model.module
         images = inputs.get("images", None)
         fwd = dict(input_ids=inputs["input_ids"], labels=inputs["labels"], attention_mask=inputs.get("attention_mask"), images=images)
-        tower_feats = None
+        pipe = inputs.get("_pipeline")          # software pipeline across micro-batches (see _graph_static_inputs): teacher logits and tower
+        tower_feats = None                      # features of THIS batch were produced during the previous micro-batch
         with torch.no_grad():
-            if self.share_tower and images is not None:
-                dev = model.device
-                imgs = torch.stack([im.to(dev, non_blocking=True) for im in images]) if not torch.is_tensor(images) else images.to(dev)
-                fwd["images"] = imgs
-                tower_feats = model.get_image_tower()(imgs.to(model.dtype))
+            if pipe is not None:
+                fwd["images"] = inputs["images"]
+                tower_feats = pipe["tower_cur"]
+            elif self.share_tower and images is not None:
+                fwd["images"] = self._device_images(model, images)
+                tower_feats = model.get_image_tower()(fwd["images"].to(model.dtype))
             plan = inputs.get("splice_plan")
             if plan is None and images is not None and model.get_image_tower() is not None and \
                     model.get_image_tower().num_patches == ref.get_image_tower().num_patches:
                 plan = model.make_splice_plan(fwd["input_ids"], fwd["attention_mask"], fwd["labels"])     # one host plan for both models
-        # The frozen teacher forward and the student forward are independent until the loss: fork the teacher onto a side stream so
-        # the student's small kernels (H=1024: launch/tail bound) fill the gaps of the teacher's machine-filling GEMMs.  Inside a
-        # CUDA-graph capture this becomes a fork/join in the graph.
+        # The frozen teacher forward is independent of the student until the loss: it runs on a side stream so the student's small
+        # kernels (H=1024: launch/tail bound) fill the gaps of the teacher's machine-filling GEMMs (a fork/join inside the CUDA graph).
+        # Pipelined form: the side stream computes the teacher for the NEXT micro-batch while the main stream runs the student's
+        # forward, the loss and the backward of THIS one against teacher logits produced one micro-batch earlier.
         main = torch.cuda.current_stream()
         side = self._teacher_stream if self.overlap_teacher else None
         if side is not None:
             side.wait_stream(main)
         with torch.no_grad(), torch.cuda.stream(side if side is not None else main):
-            t = ref.forward_hidden(**fwd, tower_features=tower_feats, plan=plan)
-            th = t["hidden"]
-            t_logits = K.mm_nt(th.reshape(-1, th.shape[-1]), ref.lm_head.weight)              # teacher logits, bf16 [N, Vt]
+            if pipe is not None:
+                nxt = pipe["next"]
+                tower_next = model.get_image_tower()(nxt["images"].to(model.dtype))
+                t_next, _ = self._teacher_forward(dict(input_ids=nxt["input_ids"], labels=nxt["labels"], attention_mask=nxt.get("attention_mask"),
+                                                       images=nxt["images"]), tower_next, nxt["splice_plan"])
+                t_logits, t_shape = pipe["t_cur"], pipe["t_shape"]
+            else:
+                t_logits, t_shape = self._teacher_forward(fwd, tower_feats, plan)
         s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"), plan=plan)
-        if side is not None:
+        if side is not None and pipe is None:
             main.wait_stream(side)
             t_logits.record_stream(main)
-            th.record_stream(main)
         labels = s["labels"]
-        if s["hidden"].shape[:2] != labels.shape or th.shape[:2] != labels.shape:
+        if s["hidden"].shape[:2] != labels.shape or tuple(t_shape) != tuple(labels.shape):
             raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
         vocab = min(self.kd_vocab, model.config.vocab_size, t_logits.shape[-1])
         w_ce = 0.0 if self.loss_type == "only_kd" else 1.0
@@ -167,6 +186,8 @@ class AlignTrainer(BaseTrainer):
         outputs = {"loss": losses.detach().mean(), "loss/align": align_loss.detach().mean(),
                    "loss/moe_balance": moe_loss.detach().mean(), "loss/lm": policy_sft_loss.detach().mean()}
         self.store_metrics(outputs, train_eval="train")
+        if pipe is not None:
+            pipe["t_next"], pipe["tower_next"] = t_next, tower_next      # copied into the "current" buffers after the backward
         if return_outputs:
             return losses.mean(), outputs
         return losses.mean()
@@ -178,7 +199,7 @@ class AlignTrainer(BaseTrainer):
             self._stored_metrics[train_eval][key].append(value)
 
     # ---- CUDA-graph plumbing (see BaseTrainer._graphed_micro_batch) -------------------------------------------------
-    def _graph_signature(self, inputs):
+    def _graph_signature(self, inputs, next_inputs=None):
         images = inputs.get("images")
         if images is None or inputs.get("moe_noise") is not None:
             return None
@@ -191,17 +212,15 @@ class AlignTrainer(BaseTrainer):
             return None                   # padded batches take the masked-attention path eagerly
         n_img = len(images) if not torch.is_tensor(images) else images.shape[0]
         ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
-        return ("align", tuple(ids.shape), tuple(plan["src"].shape), n_img, ish, plan["has_mask"], plan["has_labels"], self.loss_type)
+        sig = ("align", tuple(ids.shape), tuple(plan["src"].shape), n_img, ish, plan["has_mask"], plan["has_labels"], self.loss_type)
+        if next_inputs is not None and self.overlap_teacher and self.pipeline_teacher:
+            nsig = self._graph_signature(next_inputs)
+            if nsig == sig:
+                return sig + ("pipelined",)
+        return sig
 
-    def _graph_static_inputs(self, inputs, static):
-        dev = self.model.device
+    def _fill_static(self, static, inputs):
         images, plan = inputs["images"], inputs["splice_plan"]
-        if static is None:
-            n = len(images) if not torch.is_tensor(images) else images.shape[0]
-            ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
-            static = dict(input_ids=inputs["input_ids"], labels=inputs["labels"], attention_mask=inputs.get("attention_mask"),
-                          images=torch.empty((n,) + ish, dtype=self.model.dtype, device=dev),
-                          splice_plan={k: (torch.empty_like(v) if torch.is_tensor(v) else v) for k, v in plan.items()})
         if torch.is_tensor(images):
             static["images"].copy_(images, non_blocking=True)
         else:
@@ -210,7 +229,52 @@ class AlignTrainer(BaseTrainer):
         for k, v in plan.items():
             if torch.is_tensor(v):
                 static["splice_plan"][k].copy_(v, non_blocking=True)
+
+    def _new_static(self, inputs):
+        dev = self.model.device
+        images, plan = inputs["images"], inputs["splice_plan"]
+        n = len(images) if not torch.is_tensor(images) else images.shape[0]
+        ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
+        return dict(input_ids=inputs["input_ids"], labels=inputs["labels"], attention_mask=inputs.get("attention_mask"),
+                    images=torch.empty((n,) + ish, dtype=self.model.dtype, device=dev),
+                    splice_plan={k: (torch.empty_like(v) if torch.is_tensor(v) else v) for k, v in plan.items()})
+
+    def _graph_static_inputs(self, inputs, static, next_inputs=None, pipelined=False):
+        if static is None:
+            static = self._new_static(inputs)
+            if pipelined:
+                nxt = self._new_static(next_inputs)
+                # teacher logits / tower features of the CURRENT batch: filled by the prologue (eager) or by the previous replay
+                with torch.no_grad():
+                    self._fill_static(nxt, inputs)
+                    tower = self.model.get_image_tower()(nxt["images"].to(self.model.dtype))
+                    t_cur, t_shape = self._teacher_forward(dict(input_ids=inputs["input_ids"], labels=inputs["labels"],
+                                                                attention_mask=inputs.get("attention_mask"), images=nxt["images"]),
+                                                           tower, nxt["splice_plan"])
+                static["_pipeline"] = dict(next=nxt, t_cur=t_cur.clone(), tower_cur=tower.clone(), t_shape=tuple(t_shape), holds=inputs)
+        self._fill_static(static, inputs)
+        if pipelined:
+            pipe = static["_pipeline"]
+            if pipe["holds"] is not inputs:       # the "current" buffers do not belong to this batch (first call / caller skipped ahead)
+                with torch.no_grad():
+                    tower = self.model.get_image_tower()(static["images"].to(self.model.dtype))
+                    t_cur, _ = self._teacher_forward(dict(input_ids=inputs["input_ids"], labels=inputs["labels"],
+                                                          attention_mask=inputs.get("attention_mask"), images=static["images"]),
+                                                     tower, static["splice_plan"])
+                    pipe["t_cur"].copy_(t_cur)
+                    pipe["tower_cur"].copy_(tower)
+            self._fill_static(pipe["next"], next_inputs)
+            pipe["holds"] = next_inputs           # after this replay the "current" buffers describe next_inputs
         return static
+
+    def _graph_epilogue(self, static):
+        """Captured at the end of the graph: hand the side stream's results (teacher logits / tower features of the next batch) over."""
+        pipe = static.get("_pipeline")
+        if pipe is not None:
+            main = torch.cuda.current_stream()
+            main.wait_stream(self._teacher_stream)
+            pipe["t_cur"].copy_(pipe["t_next"])
+            pipe["tower_cur"].copy_(pipe["tower_next"])
 
     def log(self, logs: Dict[str, float]) -> None:
         train_eval = "train" if "loss" in logs else "eval"

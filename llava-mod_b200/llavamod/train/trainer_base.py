@@ -81,16 +81,18 @@ class BaseTrainer:
     def compute_loss(self, model, inputs, return_outputs=False):
         raise NotImplementedError
 
-    def training_step(self, model, inputs):
+    def training_step(self, model, inputs, next_inputs=None):
         """forward + backward of one micro-batch; the optimizer step happens every ``gradient_accumulation_steps`` calls.
-        Gradients are accumulated UNSCALED; 1/(accum*world) is folded into the AdamW kernel."""
+        Gradients are accumulated UNSCALED; 1/(accum*world) is folded into the AdamW kernel.
+        ``next_inputs`` (optional look-ahead, the batch the NEXT call will receive) lets the trainer run the frozen teacher one
+        micro-batch ahead, overlapped with this micro-batch's student forward/backward."""
         opt = self.create_optimizer()
         model.train()
         if self._accum == 0:
             opt.zero_grad()
         loss = None
         if self.use_cuda_graphs and hasattr(self, "_graph_signature"):
-            loss = self._graphed_micro_batch(model, inputs)
+            loss = self._graphed_micro_batch(model, inputs, next_inputs)
         if loss is None:
             loss = self.compute_loss(model, inputs)
             loss.backward()
@@ -102,14 +104,18 @@ class BaseTrainer:
         return loss.detach()
 
     # ---- CUDA-graph replay of one micro-batch ----------------------------------------------------------------------
-    def _graphed_micro_batch(self, model, inputs):
+    def _graphed_micro_batch(self, model, inputs, next_inputs=None):
         """Returns the loss tensor (detached, static buffer clone) or None when this batch must run eagerly.
         Subclasses provide ``_graph_signature(inputs)`` (hashable, or None = not capturable) and
         ``_graph_static_inputs(inputs, static=None)`` (allocate / refill the static device inputs)."""
         import torch
-        sig = self._graph_signature(inputs)
+        try:
+            sig = self._graph_signature(inputs, next_inputs)
+        except TypeError:
+            sig = self._graph_signature(inputs)
         if sig is None:
             return None
+        pipelined = isinstance(sig, tuple) and sig[-1] == "pipelined"
         ent = self._graphs.get(sig)
         if ent is None:
             ent = self._graphs[sig] = {"warm": 0}
@@ -117,7 +123,7 @@ class BaseTrainer:
             ent["warm"] += 1
             if ent["warm"] <= 2:                         # eager warm-up (lazy init, autotune, workspace allocation)
                 return None
-            static = self._graph_static_inputs(inputs, None)
+            static = self._graph_static_inputs(inputs, None, next_inputs, pipelined) if pipelined else self._graph_static_inputs(inputs, None)
             torch.cuda.synchronize()
             from .. import _C
             g = torch.cuda.CUDAGraph()
@@ -127,12 +133,17 @@ class BaseTrainer:
                 with torch.cuda.graph(g):
                     loss, outputs = self.compute_loss(model, static, return_outputs=True)
                     loss.backward()
+                    if hasattr(self, "_graph_epilogue"):
+                        self._graph_epilogue(static)
             finally:
                 self._suppress_store = False
             ent.update(graph=g, static=static, loss=loss.detach(), outputs={k: v for k, v in outputs.items()},
                        launches=_C.launch_count() - n0)
             # the capture pass does not execute: fall through to a replay for this very batch
-        self._graph_static_inputs(inputs, ent["static"])
+        if pipelined:
+            self._graph_static_inputs(inputs, ent["static"], next_inputs, True)
+        else:
+            self._graph_static_inputs(inputs, ent["static"])
         ent["graph"].replay()
         self.graph_replayed_launches += ent["launches"]
         self.store_metrics({k: (v.clone() if hasattr(v, "clone") else v) for k, v in ent["outputs"].items()}, train_eval="train")
