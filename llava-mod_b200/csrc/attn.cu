@@ -8,9 +8,10 @@
 //   warp 0 lane 0 : TMA producer -- Q tile once, K/V blocks of 64 keys through a 2-stage 128B-swizzled ring
 //   warp 1 lane 0 : MMA issuer   -- S_j = Q K_j^T (SS, M=128 N=64 K=16 x hd/16) into one of two S buffers in TMEM;
 //                                   O += P_j V_j (TS: A = P_j read from TMEM, B = V_j MN-major from smem, N = hd)
-//   warps 2..5    : softmax      -- one thread per query row (TMEM lane): tcgen05.ld S row -> scale, causal / length mask, running max,
-//                                   exp2, row sum -> P (bf16x2) written back over S with tcgen05.st; O rescaled in TMEM when the running
-//                                   max moved (skipped warp-uniformly when it did not); epilogue O / l -> bf16 -> global, LSE
+//   warps 2..9    : softmax      -- two threads per query row (TMEM lane = row; warps 2-5 take key columns 0-31 of each block, warps 6-9
+//                                   columns 32-63): tcgen05.ld half an S row -> mask, block max (halves exchanged through smem), exp2, row sum
+//                                   -> P (bf16x2) written back over S with tcgen05.st; each group rescales its half of O in TMEM when a
+//                                   running max moved (skipped warp-uniformly otherwise); epilogue O / l -> bf16 -> global, LSE
 // TMEM columns: S0 | S1 (64 each, P aliases its S) | O (hd).  All tensor-core work is issued by a single thread; tcgen05 executes MMAs in
 // issue order, which is what makes the S/P aliasing safe (S_{j+2} is issued after P_j V_j).
 #include "tc05.cuh"
@@ -18,7 +19,7 @@
 namespace {
 
 constexpr int BQ = 128, BKV = 64;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -34,6 +35,12 @@ __device__ __forceinline__ uint32_t attn_idesc(int n, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                  "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnParams p) {
@@ -44,6 +51,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], p_full[2], pv_done;
   __shared__ uint32_t tmem_slot;
+  __shared__ float xmax[2][2][BQ], xsum[2][BQ];        // row-max exchange (per S buffer, per column group) and final row-sum exchange
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -63,7 +71,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); }
     mbar_init(&pv_done, 1);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_q) : "memory");
@@ -128,75 +136,89 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       umma_commit(&pv_done);
     }
   } else if (warp >= 2) {
-    // ===================== softmax / correction / epilogue: one thread per query row =====================
+    // ===================== softmax / correction / epilogue: TWO threads per query row =====================
+    // warps 2..5 (group 0) own key columns [0,32) of every S block and output columns [0,HD/2); warps 6..9 (group 1) the other halves.
+    // The two threads of a row exchange their block maxima through shared memory (one 256-thread named barrier per block); the row sum
+    // stays split until the epilogue.  Half the per-thread work and twice the warps of the one-thread-per-row version.
     const int q = warp & 3;                           // TMEM lane quarter of this warp
+    const int g = (warp - 2) >> 2;                    // column group
     const int r = q * 32 + lane;                      // row within the query block == TMEM lane
     const int qrow = q0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    constexpr int HC = HD / 2;                        // O columns per group
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
       mbar_wait_warp(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sv[BKV];
-      tmem_ld32(tS0 + s * BKV + lane_off, sv);
-      tmem_ld32(tS0 + s * BKV + 32 + lane_off, sv + 32);
-      const int kv0 = j * BKV;
-      const bool need_mask = (p.causal && kv0 + BKV - 1 > q0) || (kv0 + BKV > p.T);
-      float mx = m;
+      uint32_t sv[32];
+      tmem_ld32(tS0 + s * BKV + g * 32 + lane_off, sv);
+      const int kv0 = j * BKV + g * 32;
+      const bool need_mask = (p.causal && kv0 + 31 > q0) || (kv0 + 32 > p.T);
+      float mx_loc = -INFINITY;
+      if (need_mask) {
 #pragma unroll
-      for (int c = 0; c < BKV; ++c) {
-        float x = __uint_as_float(sv[c]) * p.scale_log2;
-        if (need_mask) {
+        for (int c = 0; c < 32; ++c) {
           const int kv = kv0 + c;
+          float x = __uint_as_float(sv[c]);
           if (kv >= p.T || (p.causal && kv > qrow)) x = -INFINITY;
+          sv[c] = __float_as_uint(x);
+          mx_loc = fmaxf(mx_loc, x);
         }
-        sv[c] = __float_as_uint(x);
-        mx = fmaxf(mx, x);
-      }
-      const float m_use = (mx == -INFINITY) ? 0.f : mx;     // fully masked row (only rows >= T): keep everything finite
-      const float alpha = ex2f(m - m_use);                   // m = -inf on the first block -> 0
-      float rs = 0.f;
-      uint32_t pk[BKV / 2];
+      } else {
 #pragma unroll
-      for (int c = 0; c < BKV; c += 2) {
-        const float p0 = ex2f(__uint_as_float(sv[c]) - m_use), p1 = ex2f(__uint_as_float(sv[c + 1]) - m_use);
-        rs += p0 + p1;
+        for (int c = 0; c < 32; ++c) mx_loc = fmaxf(mx_loc, __uint_as_float(sv[c]));
+      }
+      xmax[s][g][r] = mx_loc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mx = fmaxf(m, fmaxf(mx_loc, xmax[s][g ^ 1][r]) * p.scale_log2);   // running max in scaled-log2 units (scale > 0)
+      const float m_use = (mx == -INFINITY) ? 0.f : mx;     // fully masked so far (rows >= T only): keep everything finite
+      const float alpha = ex2f(m - m_use);                   // m = -inf on the first block -> 0
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const float p0 = ex2f(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_use));
+        const float p1 = ex2f(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_use));
+        rs0 += p0; rs1 += p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
-      l = l * alpha + rs;
+      l = l * alpha + (rs0 + rs1);
       const bool moved = mx > m;
       m = mx;
       if (j > 0) {
         mbar_wait_warp(&pv_done, (j - 1) & 1);               // O holds blocks 0..j-1
         tc_fence_after();
-        if (__any_sync(0xffffffffu, moved)) {                // rescale O only when some row of this warp raised its max
+        if (__any_sync(0xffffffffu, moved)) {                // rescale this group's half of O only when a row of the warp raised its max
 #pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
+          for (int c = 0; c < HC / 32; ++c) {
             uint32_t o[32];
-            tmem_ld32(tO + c * 32 + lane_off, o);
+            tmem_ld32(tO + g * HC + c * 32 + lane_off, o);
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tO + c * 32 + lane_off, o);
+            tmem_st32(tO + g * HC + c * 32 + lane_off, o);
           }
         }
       }
-      tmem_st32(tS0 + s * BKV + lane_off, pk);               // P_j over the first 32 columns of S_j
+      tmem_st16(tS0 + s * BKV + g * 16 + lane_off, pk);      // P_j (bf16x2) over the start of S_j: group g -> columns [16g, 16g+16)
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[s]);
     }
-    // ---- epilogue ----
+    // ---- epilogue: combine the two partial row sums, normalise, store this group's half of the head dimension ----
+    xsum[g][r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float lt = l + xsum[g ^ 1][r];
     mbar_wait_warp(&pv_done, (nblk - 1) & 1);
     tc_fence_after();
-    const float inv = (l > 0.f) ? 1.f / l : 0.f;
+    const float inv = (lt > 0.f) ? 1.f / lt : 0.f;
     const bool ok = qrow < p.T;
-    __nv_bfloat16* orow = p.out + (int64_t)(row_base + qrow) * p.ld_o + col_q;
+    __nv_bfloat16* orow = p.out + (int64_t)(row_base + qrow) * p.ld_o + col_q + g * HC;
 #pragma unroll
-    for (int c = 0; c < HD / 32; ++c) {
+    for (int c = 0; c < HC / 32; ++c) {
       uint32_t o[32];
-      tmem_ld32(tO + c * 32 + lane_off, o);
+      tmem_ld32(tO + g * HC + c * 32 + lane_off, o);
       if (ok) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -209,7 +231,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
       }
     }
-    if (ok && p.lse) p.lse[((int64_t)b * p.nh + h) * p.T + qrow] = (m + lg2f(l)) * LN2_F;
+    if (g == 0 && ok && p.lse) p.lse[((int64_t)b * p.nh + h) * p.T + qrow] = (m + lg2f(lt)) * LN2_F;
   }
   tc_fence_before();
   __syncthreads();
