@@ -18,6 +18,19 @@ import torch.distributed as dist
 from .engine import TrainState, cosine_lr
 
 
+def _with_lookahead(iterable):
+    """(item, next_item) pairs; next_item is None for the last element."""
+    it = iter(iterable)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return
+    for nxt in it:
+        yield cur, nxt
+        cur = nxt
+    yield cur, None
+
+
 class TrainerState:
     def __init__(self):
         self.global_step = 0
@@ -171,9 +184,9 @@ class BaseTrainer:
         while not done:
             if hasattr(dl.sampler, "set_epoch"):
                 dl.sampler.set_epoch(epoch)
-            for batch in dl:
+            for batch, nxt in _with_lookahead(dl):
                 before = self.state.global_step
-                loss = self.training_step(self.model, batch)
+                loss = self.training_step(self.model, batch, nxt)     # look-ahead: the frozen teacher runs one micro-batch ahead
                 tr_loss += float(loss); n_loss += 1
                 if self.state.global_step != before:
                     s = self.state.global_step
