@@ -158,7 +158,7 @@ def linear(x, w, bias=None, wgrad=None, bgrad=None):
 import os as _os
 
 ATTN_HEAD_DIMS = (64, 128)
-ATTN_BWD_TCGEN05 = _os.environ.get("LLAVAMOD_ATTN_BWD", "flash") == "tcgen05"
+ATTN_BWD_TCGEN05 = _os.environ.get("LLAVAMOD_ATTN_BWD", "tcgen05") != "flash"
 
 
 def attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale=None, need_lse=False):
@@ -172,8 +172,9 @@ def attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale=None, need_lse=False):
 
 
 class AttnFn(Function):
-    """Qwen2SdpaAttention core (modeling_qwen2.py:713-721): our tcgen05 forward (lmod_attn_fwd); backward = flash-attn 2 library kernel
-    by default, our tcgen05 backward (lmod_attn_bwd) with LLAVAMOD_ATTN_BWD=tcgen05.  dq|dk|dv come back as one fused buffer."""
+    """Qwen2SdpaAttention core (modeling_qwen2.py:713-721): our tcgen05 forward (lmod_attn_fwd) and backward (lmod_attn_bwd); dq|dk|dv
+    come back as one fused buffer.  LLAVAMOD_ATTN_BWD=flash swaps in flash-attn 2's library backward (the A/B arm of the throughput
+    report in tests/test_attn_gpu.py, not a product path)."""
 
     @staticmethod
     def forward(ctx, qkv, B, T, nh, nkv, hd, causal, scale):
@@ -189,8 +190,7 @@ class AttnFn(Function):
         B, T, nh, nkv, hd, causal, scale = ctx.dims
         if ATTN_BWD_TCGEN05:
             return attention_bwd(qkv, out, _c(dout), lse, B, T, nh, nkv, hd, causal, scale), None, None, None, None, None, None, None
-        # default this round: flash-attn 2's library backward, fed with OUR forward's output and log-sum-exp and writing dq|dk|dv
-        # straight into one fused buffer (our tcgen05 backward is parity-green but 1.5-2.6x slower)
+        # A/B arm only: flash-attn 2's library backward fed with OUR forward's output and log-sum-exp
         from flash_attn.flash_attn_interface import _wrapped_flash_attn_backward
         q = qkv[:, : nh * hd].view(B, T, nh, hd)
         k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)

@@ -17,3 +17,12 @@ ref.backward(go.float())
 for name, sl in (("dq", slice(0, nh * hd)), ("dk", slice(nh * hd, (nh + nkv) * hd)), ("dv", slice((nh + nkv) * hd, None))):
     a, r = qkv.grad[:, sl].float(), x.grad[:, sl]
     print(name, "rel err", (a - r).norm().item() / r.norm().item(), flush=True)
+# error map of dq per (64-query block, head)
+a, r = qkv.grad[:, : nh * hd].float().view(B, T, nh, hd), x.grad[:, : nh * hd].view(B, T, nh, hd)
+for bb in range(B):
+    for h in range(nh):
+        errs = []
+        for q0 in range(0, T, 64):
+            d = (a[bb, q0:q0 + 64, h] - r[bb, q0:q0 + 64, h]).norm().item() / (r[bb, q0:q0 + 64, h].norm().item() + 1e-9)
+            errs.append("%.3f" % d)
+        print("b", bb, "h", h, " ".join(errs))
