@@ -248,6 +248,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # the one JSON line is all rank 0 may print on stdout: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     wl_name = args.workload
@@ -373,7 +376,7 @@ def run_ours(args):
         "config": {"workload": wl_name, "student": wl["student"] + "-%dE-top2" % wl["experts"], "teacher": wl["teacher"], "vision": wl["clip"],
                    "seq_len": T, "micro_batch": 1, "grad_accum": accum, "global_batch": accum * world, "loss": "kd_lm (mimic KL + LM + aux)",
                    "parallelism": "dp%d" % world, "l2": "working set per micro-batch (15.4 GB of teacher weights) >> 126 MB L2; no explicit flush",
-                   "gemm": "hand-written tcgen05+TMA GEMM / grouped expert GEMM and tcgen05 flash-attention forward (liblmod_b200); flash-attn 2 library only for the student attention BACKWARD; every other op liblmod_b200",
+                   "gemm": "hand-written tcgen05+TMA GEMM / grouped expert GEMM and tcgen05 flash-attention forward AND backward (liblmod_b200); no library GEMM or attention kernel on the path",
                    "cuda_graphs": bool(trainer.use_cuda_graphs)},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": 2 * accum * (img_bytes + plan_bytes), "d2h_bytes_per_step": 4,
