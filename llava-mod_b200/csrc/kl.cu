@@ -14,13 +14,16 @@
 //   * two CTAs are resident per SM (<= 2 x 76 KB smem) so one CTA's loads overlap the other's math.
 //   * rows whose KD mask and CE mask are both 0 contribute nothing (reference multiplies by 0):
 //     their loads are skipped and their gradient slice is zero-filled.
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace {
 
 constexpr int KL_CHUNKS = 4;       // mbarrier-tracked load chunks per slice
 constexpr int KL_MAX_CS = 8;
+constexpr int KL_DEFAULT_MODE = 0;      // measured (profiles/kl_modes_r1.txt): sb256 0.67 ms, db256 1.10 ms, db512 1.24 ms (all rows active)
 
 struct KlParams {
   const __nv_bfloat16* s;
@@ -66,19 +69,22 @@ __device__ __forceinline__ void accum_pair(uint32_t sw, uint32_t tw, float nms, 
   a = fmaf(et1, s1, a);
 }
 
-template <int KL_THREADS>
-__global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams p) {
+// NBUF = 1 (default): one slice buffer, two CTAs per SM hide each other's loads AND each other's barrier waits (33 co-resident clusters).
+// NBUF = 2 (LMOD_KL_MODE=db256/db512, experiment kept for the record): one CTA per SM with two slice buffers, the loads of the cluster's
+// NEXT active row issued before the math of the current one.  Measured 1.6-1.8x SLOWER: with one CTA per SM nothing fills the SM while
+// the CTA sits in __syncthreads / barrier.cluster (22 % of warp samples), and only 15 clusters of 8 single-CTA SMs fit the GPCs.
+template <int KL_THREADS, int NBUF>
+__global__ void __launch_bounds__(KL_THREADS, NBUF == 2 ? 1 : 2) kl_fused_kernel(const KlParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(16) Xchg xchg[2];
-  __shared__ __align__(8) uint64_t bars[KL_CHUNKS];
+  __shared__ __align__(8) uint64_t bars_all[NBUF][KL_CHUNKS];
   __shared__ float red[7][KL_THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank(), cs = cluster_nctarank();
   const uint32_t cid = cluster_id_x(), ncl = cluster_nclusters_x();
 
-  uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
-  uint4* t_buf = reinterpret_cast<uint4*>(smem_raw + (size_t)p.slice * 2);
+  const size_t buf_bytes = (size_t)p.slice * 4;                 // student + teacher slice
 
   // this CTA's slice of the vocabulary
   const int v0 = (int)rank * p.slice;
@@ -88,7 +94,8 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
   const int cvec = ((nvec + KL_CHUNKS - 1) / KL_CHUNKS);        // vectors per chunk
 
   if (tid == 0) {
-    for (int c = 0; c < KL_CHUNKS; ++c) mbar_init(&bars[c], 1);
+    for (int b = 0; b < NBUF; ++b)
+      for (int c = 0; c < KL_CHUNKS; ++c) mbar_init(&bars_all[b][c], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -119,22 +126,49 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
       }
       continue;
     }
-    const uint32_t par = it_active & 1u;
-    ++it_active;
+    const uint32_t xi = it_active & 1u;                                        // exchange slot
+    const uint32_t bsel = (NBUF == 2) ? (it_active & 1u) : 0u;                  // slice buffer
+    const uint32_t par = (NBUF == 2) ? ((it_active >> 1) & 1u) : (it_active & 1u);
+    uint64_t* bars = bars_all[bsel];
+    uint4* s_buf = reinterpret_cast<uint4*>(smem_raw + bsel * buf_bytes);
+    uint4* t_buf = reinterpret_cast<uint4*>(smem_raw + bsel * buf_bytes + (size_t)p.slice * 2);
 
     // ---- issue the slice loads (1-D TMA bulk copies), chunked so math can start early ----
-    if (tid == 0 && nvec > 0) {
-      const __nv_bfloat16* srow = p.s + row * p.ld_s + v0;
-      const __nv_bfloat16* trow = p.t + row * p.ld_t + v0;
+    auto issue_row = [&](int64_t r, uint32_t b) {
+      if (nvec <= 0) return;
+      const __nv_bfloat16* srow = p.s + r * p.ld_s + v0;
+      const __nv_bfloat16* trow = p.t + r * p.ld_t + v0;
+      uint4* sb = reinterpret_cast<uint4*>(smem_raw + b * buf_bytes);
+      uint4* tb = reinterpret_cast<uint4*>(smem_raw + b * buf_bytes + (size_t)p.slice * 2);
       for (int c = 0; c < KL_CHUNKS; ++c) {
-        int b = c * cvec, e = min(nvec, b + cvec);
-        if (e <= b) { mbar_arrive(&bars[c]); continue; }
-        uint32_t bytes = (uint32_t)(e - b) * 16u;
-        mbar_expect_tx(&bars[c], 2 * bytes);
-        bulk_g2s(s_buf + b, srow + (size_t)b * 8, bytes, &bars[c]);
-        bulk_g2s(t_buf + b, trow + (size_t)b * 8, bytes, &bars[c]);
+        int cb = c * cvec, ce = min(nvec, cb + cvec);
+        if (ce <= cb) { mbar_arrive(&bars_all[b][c]); continue; }
+        uint32_t bytes = (uint32_t)(ce - cb) * 16u;
+        mbar_expect_tx(&bars_all[b][c], 2 * bytes);
+        bulk_g2s(sb + cb, srow + (size_t)cb * 8, bytes, &bars_all[b][c]);
+        bulk_g2s(tb + cb, trow + (size_t)cb * 8, bytes, &bars_all[b][c]);
       }
+    };
+    if (NBUF == 1) {
+      if (tid == 0) issue_row(row, 0);
+    } else if (warp == 0) {
+      // the first active row loads itself; every active row then looks ahead (32 candidate rows per ballot) for the cluster's next
+      // active row and starts ITS loads into the other buffer, which the previous row released at its closing __syncthreads
+      if (it_active == 0 && lane == 0) issue_row(row, 0);
+      int64_t nxt = -1;
+      for (int64_t base = row; base + ncl < p.n_rows; base += 32 * (int64_t)ncl) {
+        const int64_t r = base + (int64_t)(lane + 1) * ncl;
+        bool act = false;
+        if (r < p.n_rows) {
+          act = p.distill_all || (p.labels[r] != LMOD_IGNORE_INDEX);
+          if (!act && (r % p.seq_len) + 1 < p.seq_len) act = p.labels[r + 1] != LMOD_IGNORE_INDEX;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (m) { nxt = base + (int64_t)__ffs(m) * ncl; break; }
+      }
+      if (lane == 0 && nxt >= 0) issue_row(nxt, bsel ^ 1u);
     }
+    ++it_active;
 
     // ---- pass A: slice max (and min of s, to detect -inf logits) ----
     uint32_t mxs = 0xff80ff80u, mxt = 0xff80ff80u, mns = 0x7f807f80u;   // bf16x2 (-inf,-inf) / (+inf,+inf)
@@ -210,7 +244,7 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
         Xchg x;
         x.ms = (nvec > 0) ? ms : -INFINITY; x.mt = (nvec > 0) ? mt : -INFINITY;
         x.zs = a; x.zt = b; x.a = c; x.slab = slab; x.pad0 = k; x.pad1 = 0.f;
-        xchg[par] = x;
+        xchg[xi] = x;
       }
     }
     // ---- cluster exchange through distributed shared memory ----
@@ -219,7 +253,7 @@ __global__ void __launch_bounds__(KL_THREADS, 2) kl_fused_kernel(const KlParams 
     {
       float r_ms = -INFINITY, r_mt = -INFINITY, r_zs = 0.f, r_zt = 0.f, r_a = 0.f, r_sl = 0.f, r_zk = 0.f;
       if ((uint32_t)lane < cs) {
-        const float* base = reinterpret_cast<const float*>(&xchg[par]);
+        const float* base = reinterpret_cast<const float*>(&xchg[xi]);
         r_ms = dsmem_ld_f32(base + 0, lane); r_mt = dsmem_ld_f32(base + 1, lane);
         r_zs = dsmem_ld_f32(base + 2, lane); r_zt = dsmem_ld_f32(base + 3, lane);
         r_a = dsmem_ld_f32(base + 4, lane);  r_sl = dsmem_ld_f32(base + 5, lane); r_zk = dsmem_ld_f32(base + 6, lane);
@@ -327,13 +361,14 @@ extern "C" int lmod_kl_finalize(const float* row_out, const int64_t* labels, int
   return LMOD_OK;
 }
 
-template <int T>
+template <int T, int NB>
 int kl_launch(KlParams p, int cs, size_t smem, int64_t n_rows, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(kl_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LMOD_CUDA_OK(cudaFuncSetAttribute(kl_fused_kernel<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done = true;
   }
+  smem *= NB;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -344,12 +379,13 @@ int kl_launch(KlParams p, int cs, size_t smem, int64_t n_rows, cudaStream_t stre
   static int cached_clusters[2] = {0, 0};        // per cluster size (1 / 8): queried once, outside any stream capture
   int& max_clusters = cached_clusters[cs == 1 ? 0 : 1];
   if (max_clusters <= 0) {
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_fused_kernel<T>, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_fused_kernel<T, NB>, &cfg);
     if (e != cudaSuccess || max_clusters <= 0) { (void)cudaGetLastError(); max_clusters = lmod_num_sms() / cs; }
+    if (getenv("LMOD_KL_VERBOSE")) fprintf(stderr, "[lmod] kl_fused_kernel<%d,%d>: cluster %d, %zu B smem, %d co-resident clusters\n", T, NB, cs, smem, max_clusters);
   }
   int64_t ncl = n_rows < max_clusters ? n_rows : max_clusters;
   cfg.gridDim = dim3((unsigned)(ncl * cs));
-  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_fused_kernel<T>, p));
+  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_fused_kernel<T, NB>, p));
   lmod_count_launch();
   return LMOD_OK;
 }
@@ -377,6 +413,11 @@ extern "C" int lmod_kl_fwd_bwd(const void* s_logits, int64_t ld_s, const void* t
   p.ld_s = ld_s; p.ld_t = ld_t; p.ld_d = ld_d; p.n_rows = n_rows; p.seq_len = seq_len;
   p.vocab = (int)vocab; p.slice = slice; p.distill_all = distill_all; p.w_kd = w_kd; p.w_ce = w_ce;
 
-  static const int kl_threads = getenv("LMOD_KL_THREADS") ? atoi(getenv("LMOD_KL_THREADS")) : 256;   // measured: 256 thr x 109 regs = 0.67 ms, 512 thr x 64 regs = 0.88 ms (all rows active)
-  return (kl_threads == 256) ? kl_launch<256>(p, cs, smem, n_rows, (cudaStream_t)stream) : kl_launch<512>(p, cs, smem, n_rows, (cudaStream_t)stream);
+  // LMOD_KL_MODE: "sb256" one slice buffer, 2 CTAs/SM (round-1 first version); "db256"/"db512" double-buffered slice, 1 CTA/SM
+  static const char* mode_env = getenv("LMOD_KL_MODE");
+  static const int mode = !mode_env ? KL_DEFAULT_MODE : (!strcmp(mode_env, "sb256") ? 0 : (!strcmp(mode_env, "db256") ? 1 : 2));
+  const bool db_fits = smem * 2 <= 220 * 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0 || !db_fits) return kl_launch<256, 1>(p, cs, smem, n_rows, st);
+  return (mode == 1) ? kl_launch<256, 2>(p, cs, smem, n_rows, st) : kl_launch<512, 2>(p, cs, smem, n_rows, st);
 }
