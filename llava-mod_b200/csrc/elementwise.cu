@@ -69,6 +69,65 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const __nv_bf
   }
 }
 
+// Same, for rows that fit the CTA's registers (H <= 128 * 8 * VPT): x (+res) is read from HBM exactly once, kept packed in registers
+// across the block reduction, and all loads of a thread are in flight together.
+template <int VPT>
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_reg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                                                      const __nv_bfloat16* __restrict__ w, int H, float eps,
+                                                                      __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ x_out,
+                                                                      float* __restrict__ rstd_out) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int hv = H >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * H);
+  const uint4* rr = res ? reinterpret_cast<const uint4*>(res + row * H) : nullptr;
+  uint4* xo = x_out ? reinterpret_cast<uint4*>(x_out + row * H) : nullptr;
+  uint4 xv[VPT], rv[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    xv[i] = make_uint4(0, 0, 0, 0); rv[i] = make_uint4(0, 0, 0, 0);
+    if (v < hv) {
+      xv[i] = ldg_nc_v4(xr + v);
+      if (rr) rv[i] = ldg_nc_v4(rr + v);
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    float f[8];
+    unpack8(xv[i], f);
+    if (rr) {
+      float g[8];
+      unpack8(rv[i], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] + g[j]);
+      xv[i] = pack8(f);
+    }
+    if (xo && v < hv) xo[v] = xv[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+  }
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / (float)H + eps);
+  if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * H);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < hv) {
+      float f[8], wf[8];
+      unpack8(xv[i], f);
+      unpack8(__ldg(wr + v), wf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = wf[j] * bf16_round(f[j] * rstd);
+      yr[v] = pack8(f);
+    }
+  }
+}
+
 // dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres)
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                                   const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
@@ -175,10 +234,9 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(__nv_bfloat16* __restrict
                                                       int backward) {
   const int half = hd >> 1, vph = half >> 3;
   const int per_row = (nh + nkv) * vph;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= rows * per_row) return;
-  const int64_t row = gid / per_row;
-  const int r = (int)(gid % per_row);
+  const int64_t row = blockIdx.x;                               // grid: (rows, ceil(per_row / 256)) -- no 64-bit divisions
+  const int r = (int)(blockIdx.y * blockDim.x + threadIdx.x);
+  if (r >= per_row) return;
   const int head = r / vph, v = r % vph;
   __nv_bfloat16* base = (head < nh) ? (q + row * ld_q + (size_t)head * hd) : (k + row * ld_k + (size_t)(head - nh) * hd);
   const int64_t pp = pos[row];
@@ -210,7 +268,9 @@ __global__ void silu_mul_fwd_kernel(const __nv_bfloat16* __restrict__ gu, int64_
   const int iv = I >> 3;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= rows * iv) return;
-  const int64_t row = gid / iv; const int v = (int)(gid % iv);
+  int64_t row; int v;
+  if (rows * iv < (int64_t)1 << 31) { const uint32_t g32 = (uint32_t)gid; row = g32 / (uint32_t)iv; v = (int)(g32 % (uint32_t)iv); }   // 32-bit divide
+  else { row = gid / iv; v = (int)(gid % iv); }
   float g[8], u[8];
   unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(gu + row * ld) + v), g);
   unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(gu + row * ld + I) + v), u);
@@ -223,7 +283,9 @@ __global__ void silu_mul_bwd_kernel(const __nv_bfloat16* __restrict__ dout, cons
   const int iv = I >> 3;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= rows * iv) return;
-  const int64_t row = gid / iv; const int v = (int)(gid % iv);
+  int64_t row; int v;
+  if (rows * iv < (int64_t)1 << 31) { const uint32_t g32 = (uint32_t)gid; row = g32 / (uint32_t)iv; v = (int)(g32 % (uint32_t)iv); }   // 32-bit divide
+  else { row = gid / iv; v = (int)(gid % iv); }
   float g[8], u[8], d[8], dg[8], du[8];
   unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(gu + row * ld) + v), g);
   unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(gu + row * ld + I) + v), u);
@@ -321,9 +383,19 @@ __global__ void __launch_bounds__(256) splice_embed_bwd_kernel(const __nv_bfloat
 extern "C" int lmod_rmsnorm_fwd(const void* x, const void* res, const void* w, int64_t rows, int64_t H, float eps, void* y, void* x_out,
                                 float* rstd, void* stream) {
   LMOD_CHECK_ARG(x && w && y && rows > 0 && H > 0 && H % 8 == 0, "lmod_rmsnorm_fwd: bad arguments (H %% 8 == 0 required)");
-  rmsnorm_fwd_kernel<<<(unsigned)rows, NORM_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
-                                                                               (const __nv_bfloat16*)w, (int)H, eps, (__nv_bfloat16*)y,
-                                                                               (__nv_bfloat16*)x_out, rstd);
+  const int hv = (int)(H / 8);
+#define LMOD_RMS_REG(VPT)                                                                                                              \
+  rmsnorm_fwd_reg_kernel<VPT><<<(unsigned)rows, NORM_THREADS, 0, (cudaStream_t)stream>>>(                                              \
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (const __nv_bfloat16*)w, (int)H, eps, (__nv_bfloat16*)y, (__nv_bfloat16*)x_out, rstd)
+  if (hv <= NORM_THREADS) LMOD_RMS_REG(1);
+  else if (hv <= 2 * NORM_THREADS) LMOD_RMS_REG(2);
+  else if (hv <= 4 * NORM_THREADS) LMOD_RMS_REG(4);
+  else if (hv <= 8 * NORM_THREADS) LMOD_RMS_REG(8);
+  else
+    rmsnorm_fwd_kernel<<<(unsigned)rows, NORM_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
+                                                                                 (const __nv_bfloat16*)w, (int)H, eps, (__nv_bfloat16*)y,
+                                                                                 (__nv_bfloat16*)x_out, rstd);
+#undef LMOD_RMS_REG
   LMOD_LAUNCH_OK();
   return LMOD_OK;
 }
@@ -347,8 +419,9 @@ extern "C" int lmod_rope(void* q, int64_t ld_q, int nh, void* k, int64_t ld_k, i
                          const void* sin_table, const int64_t* position_ids, int64_t rows, int backward, void* stream) {
   LMOD_CHECK_ARG(q && k && cos_table && sin_table && position_ids && rows > 0 && hd % 2 == 0, "lmod_rope: bad arguments");
   if (hd % 16 == 0 && ld_q % 8 == 0 && ld_k % 8 == 0 && ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0)) {
-    const int64_t nv = rows * (nh + nkv) * (hd / 16);
-    rope_vec_kernel<<<GRID1D(nv, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)q, ld_q, nh, (__nv_bfloat16*)k, ld_k, nkv, hd,
+    const int per_row = (nh + nkv) * (hd / 16);
+    const int thr = per_row >= 256 ? 256 : ((per_row + 31) / 32 * 32);
+    rope_vec_kernel<<<dim3((unsigned)rows, (unsigned)((per_row + thr - 1) / thr)), thr, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)q, ld_q, nh, (__nv_bfloat16*)k, ld_k, nkv, hd,
                                                                      (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table,
                                                                      position_ids, rows, backward);
     LMOD_LAUNCH_OK();

@@ -494,10 +494,12 @@ class MoEFn(Function):
         r = moe_route_scatter(x, wg, noise, cf, min_cap, LAYOUT_ALIGNED)
         R = r["max_rows"]
         xp, offs = r["xp"], r["offsets"]
-        h1 = torch.zeros(R, I2, dtype=x.dtype, device=x.device)
+        # only xp (and dy in the backward) are zero-filled: in the 128-aligned layout the grouped GEMM writes EVERY row below offsets[E],
+        # so the padding rows of h1 / act / y come out as exact zeros (0 @ W); rows past offsets[E] are never read by a GEMM
+        h1 = torch.empty(R, I2, dtype=x.dtype, device=x.device)
         grouped_gemm(xp, w_gu, h1, offs, 0)                            # [R,2I] = xp @ w_gu[e]^T
         act = silu_mul(h1)                                             # [R,I]
-        y = torch.zeros(R, H, dtype=x.dtype, device=x.device)
+        y = torch.empty(R, H, dtype=x.dtype, device=x.device)
         grouped_gemm(act, w_dn, y, offs, 0)                            # [R,H] = act @ w_dn[e]^T
         out = moe_gather_combine(y, r["row"], r["w"], res)
         ctx.save_for_backward(x, wg, w_gu, w_dn, xp, h1, act, y, r["row"], r["w"], r["gates"], r["idx"], r["meta"], offs)
@@ -515,12 +517,12 @@ class MoEFn(Function):
         dw = torch.empty(S, 2, dtype=torch.float32, device=dout.device)
         call("lmod_moe_combine_bwd", ptr(dout), ptr(y), ptr(row), ptr(w), S, H, ptr(dy), ptr(dw))
         g = ctx.grads
-        dact = torch.zeros(R, I2 // 2, dtype=dout.dtype, device=dout.device)
+        dact = torch.empty(R, I2 // 2, dtype=dout.dtype, device=dout.device)
         grouped_gemm(dy, w_dn, dact, offs, 1)                          # dact = dy @ w_dn[e]
         if g is not None and g.get("w_dn") is not None:
             grouped_gemm(dy, act, g["w_dn"], offs, 2, accumulate=True)  # dW_dn[e] += dy_e^T @ act_e
         dh1 = silu_mul_bwd(dact, h1)
-        dxp = torch.zeros(R, H, dtype=dout.dtype, device=dout.device)
+        dxp = torch.empty(R, H, dtype=dout.dtype, device=dout.device)
         grouped_gemm(dh1, w_gu, dxp, offs, 1)                          # dxp = dh1 @ w_gu[e]
         if g is not None and g.get("w_gu") is not None:
             grouped_gemm(dh1, xp, g["w_gu"], offs, 2, accumulate=True)  # dW_gu[e] += dh1_e^T @ xp_e
@@ -541,10 +543,10 @@ def moe_forward_nograd(x, res, wg, w_gu, w_dn, noise, cf, min_cap):
     E, I2, H = w_gu.shape
     r = moe_route_scatter(_c(x), wg, noise, cf, min_cap, LAYOUT_ALIGNED)
     R = r["max_rows"]
-    h1 = torch.zeros(R, I2, dtype=x.dtype, device=x.device)
+    h1 = torch.empty(R, I2, dtype=x.dtype, device=x.device)
     grouped_gemm(r["xp"], w_gu, h1, r["offsets"], 0)
     act = silu_mul(h1)
-    y = torch.zeros(R, H, dtype=x.dtype, device=x.device)
+    y = torch.empty(R, H, dtype=x.dtype, device=x.device)
     grouped_gemm(act, w_dn, y, r["offsets"], 0)
     return moe_gather_combine(y, r["row"], r["w"], _c(res)), r["meta"][0].clone(), r
 

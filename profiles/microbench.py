@@ -27,6 +27,27 @@ def timed(name, fn, work, unit):
     print("%-46s %8.3f ms  %9.1f %s" % (name, ms, work / (ms * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9), unit))
 
 
+_FLUSH = None
+
+
+def timed_cold(name, fn, work, unit):
+    """HBM-bound kernels: L2 (126 MB) is flushed before every repetition, each repetition timed on its own; median."""
+    global _FLUSH
+    if _FLUSH is None:
+        _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    fn()
+    ts = []
+    for _ in range(REPS):
+        _FLUSH.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    print("%-46s %8.3f ms  %9.1f %s (L2 flushed)" % (name, ms, work / (ms * 1e-3) / 1e9, unit))
+
+
 def main():
     T, V = 2048, 151936
     # teacher gate|up GEMM, student gate|up, wgrad, lm_head
@@ -58,6 +79,17 @@ def main():
         by = active * 6 * V + (T - active) * 2 * V
         d = torch.empty_like(s)
         timed("kl_fused fwd+bwd [2048,151936] " + tag, lambda: K.kl_fused(s, t, labels, T, V, 1.0, 1.0, False, dlogits=d), by, "GB/s")
+    # HBM-bound elementwise kernels at the shapes of the step (teacher H 4096; expert rows 4608 x I 2816)
+    xh = torch.randn(T, 4096, device=dev).to(torch.bfloat16); rs = torch.randn_like(xh); wn = torch.ones(4096, device=dev, dtype=torch.bfloat16)
+    timed_cold("rmsnorm fwd (+residual) [2048,4096]", lambda: K.RMSNormFn.apply(xh, rs, wn, 1e-6), 4 * T * 4096 * 2, "GB/s")
+    qkv7 = torch.randn(T, 3 * 4096, device=dev).to(torch.bfloat16)
+    cos = torch.randn(T, 128, device=dev).to(torch.bfloat16); sin = torch.randn(T, 128, device=dev).to(torch.bfloat16)
+    pos = torch.arange(T, device=dev)
+    timed_cold("rope q|k in place [2048, 2x32x128]", lambda: K.call("lmod_rope", K.ptr(qkv7), qkv7.stride(0), 32, K.ptr(qkv7[:, 4096:]), qkv7.stride(0), 32, 128,
+                                                              K.ptr(cos), K.ptr(sin), K.ptr(pos), T, 0), 2 * T * 8192 * 2, "GB/s")
+    gu = torch.randn(4608, 5632, device=dev).to(torch.bfloat16); dact = torch.randn(4608, 2816, device=dev).to(torch.bfloat16)
+    timed_cold("silu_mul fwd [4608, 2x2816]", lambda: K.silu_mul(gu), 3 * 4608 * 2816 * 2, "GB/s")
+    timed_cold("silu_mul bwd [4608, 2x2816]", lambda: K.silu_mul_bwd(dact, gu), 5 * 4608 * 2816 * 2, "GB/s")
     # router + scatter
     x = torch.randn(T, 1024, device=dev).to(torch.bfloat16)
     wg = torch.randn(4, 1024, device=dev) * 0.1

@@ -60,6 +60,31 @@ def test_student_forward_and_trainer_loss_match_oracle():
     assert abs(float(loss2) - float(ref2)) < 1e-2 * abs(float(ref2))
 
 
+@pytest.mark.parametrize("distill_all", [False, True])
+def test_qwen2_like_pair_gqa_teacher_with_wider_vocab(distill_all):
+    """Shell-default Qwen-2 shapes (shape table): GQA in both models and a teacher vocabulary LARGER than the student's, so the
+    reference's hard-coded logits[:, :, :151936] slice (align_trainer.py:473,497; here min(kd_vocab, student vocab)) really cuts columns;
+    plus --distill_all_tokens (align_trainer.py:512-515)."""
+    from llavamod.model import synthetic as S
+    arch_s = dict(S.ARCH["tiny"], num_key_value_heads=1, vocab_size=512, tie_word_embeddings=True)
+    arch_t = dict(S.ARCH["tiny"], num_key_value_heads=1, vocab_size=640, intermediate_size=320)
+    teacher = S.make_teacher(arch_t, "tiny", seed=3)
+    student = S.make_student(arch_s, "tiny", seed=4, margs=S.moe_args(), share_tower_with=teacher)
+    batch, noise = Hh.tiny_batch(student, seed=5)
+    with torch.no_grad():
+        t_out, _ = Hh.oracle_forward(teacher, batch)
+    s_out, lc = Hh.oracle_forward(student, batch, noise)
+    assert t_out["logits"].shape[-1] == 640 and s_out["logits"].shape[-1] == 512
+    ref_loss, ref_m = R.mimic_compute_loss(s_out, t_out["logits"], "kd_lm", True, distill_all, 512)
+    tr = Hh.make_trainer(student, teacher, "kd_lm")
+    tr.args.distill_all_tokens = distill_all
+    loss, m = tr.compute_loss(student, dict(batch, moe_noise=[n.cuda() for n in noise]), return_outputs=True)
+    for k in ("loss", "loss/align", "loss/lm", "loss/moe_balance"):
+        assert abs(float(m[k]) - float(ref_m[k])) < 1e-2 * abs(float(ref_m[k])) + 1e-4, (k, float(m[k]), float(ref_m[k]))
+    loss.backward()
+    torch.cuda.synchronize()
+
+
 def test_padded_batch_goes_through_masked_attention():
     student, teacher = Hh.tiny_pair()
     batch, noise = Hh.tiny_batch(student, seed=2, pad=(0, 7))
