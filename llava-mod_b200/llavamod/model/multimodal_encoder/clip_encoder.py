@@ -234,6 +234,20 @@ class CLIPVisionTower(nn.Module):
         return self.feature_select(self.image_tower.hidden_state(images, self.select_layer)).to(images.dtype)
 
     @property
+    def image_processor(self):
+        """CLIPImageProcessor for the data pipeline (reference clip_encoder.py:29: CLIPImageProcessor.from_pretrained(tower)).  Built from
+        the checkpoint's preprocessor_config.json when there is one, else from the tower's image size with CLIP's mean / std."""
+        if getattr(self, "_image_processor", None) is None:
+            from transformers import CLIPImageProcessor
+            name = self.image_tower_name
+            if isinstance(name, str) and os.path.exists(os.path.join(name, "preprocessor_config.json")):
+                self._image_processor = CLIPImageProcessor.from_pretrained(name)
+            else:
+                s = self.config.image_size
+                self._image_processor = CLIPImageProcessor(size={"shortest_edge": s}, crop_size={"height": s, "width": s})
+        return self._image_processor
+
+    @property
     def dummy_feature(self):
         return torch.zeros(1, self.hidden_size, device=self.device, dtype=self.dtype)
 

@@ -7,8 +7,8 @@ Kept: the four argument dataclasses, class dispatch by substring of the model pa
 MoE, ``moe_finetune`` picking the FineTune class, construction order (build -> initialize_moe_modules ->
 initialize_vision_modules), auto-resume from ``output_dir/checkpoint-*``, final save overwriting ``pytorch_model.bin`` with the
 full ``state_dict()``.  Replaced: HF Trainer/accelerate/DeepSpeed (see train/trainer_base.py, train/engine.py).  The CPU data
-pipeline of the reference (LazySupervisedDataset, preprocess_phi, tokenizer) is row N1 of SURVEY section 8f and not built:
-``--data_path synthetic[:N]`` serves seeded synthetic samples of the named shape.
+pipeline of the reference (LazySupervisedDataset, preprocess_phi, tokenizer; SURVEY section 8f row N1) lives in ``llavamod/data``;
+``--data_path synthetic[:N]`` serves seeded synthetic samples of the named shape without a tokenizer.
 """
 import glob
 import os
@@ -108,11 +108,29 @@ def collate(instances, pad_id=0):
     return dict(input_ids=ids, labels=labels, attention_mask=mask, images=[x["image"] for x in instances])
 
 
-def make_supervised_data_module(data_args, training_args, model):
+def load_tokenizer(model_args, training_args, name_or_path):
+    """Qwen-1.5 / Qwen-2 branch of the reference (align_train.py:360-369,436-441): slow AutoTokenizer, right padding, `<|extra_0|>` as
+    unk, pad = unk, and the conversation template picked by --version."""
+    import transformers
+    from .. import conversation as conversation_lib
+    tok = transformers.AutoTokenizer.from_pretrained(name_or_path, cache_dir=training_args.cache_dir,
+                                                     model_max_length=training_args.model_max_length, padding_side="right", use_fast=False)
+    tok.add_special_tokens({"unk_token": "<|extra_0|>"})
+    tok.pad_token = tok.unk_token
+    conversation_lib.set_default_conversation(model_args.version)
+    return tok
+
+
+def make_supervised_data_module(data_args, training_args, model, tokenizer=None):
     path = (data_args.data_path or ["synthetic"])[0]
     if not str(path).startswith("synthetic"):
-        raise NotImplementedError("the reference's JSON/image data pipeline (LazySupervisedDataset, preprocess_phi) is row N1 of "
-                                  "SURVEY section 8f and not built yet; use --data_path synthetic[:N]")
+        # SURVEY 8f row N1: the reference's lazy JSON dataset + collator (llavamod/data/dataset.py)
+        from ..data.dataset import make_supervised_data_module as make_json_module
+        if tokenizer is None:
+            raise ValueError("--data_path %s needs a tokenizer next to the policy checkpoint" % path)
+        data_args.image_processor = model.get_image_tower().image_processor
+        data_args.is_multimodal = True
+        return make_json_module(tokenizer, data_args)
     n = int(path.split(":")[1]) if ":" in path else 1024
     tower = model.get_image_tower()
     text_len = training_args.model_max_length - tower.num_patches + 1
@@ -137,9 +155,14 @@ def train(argv=None):
                                           align_args.ref_model_type, align_args.ref_pretrain_mm_mlp_adapter, device)
     training_args.moe_enable = model_args.moe_enable
     training_args.tune_mm_mlp_adapter = model_args.tune_mm_mlp_adapter
-    data_module = make_supervised_data_module(data_args, training_args, model)
+    path = (data_args.data_path or ["synthetic"])[0]
+    tokenizer = None
+    if not str(path).startswith("synthetic"):
+        tokenizer = load_tokenizer(model_args, training_args, align_args.policy_model_name_or_path)
+        model.config.pad_token_id = tokenizer.pad_token_id                               # align_train.py:437
+    data_module = make_supervised_data_module(data_args, training_args, model, tokenizer)
     trainer = AlignTrainer(model=model, ref_model=ref_model, args=training_args, loss_type=align_args.loss_type,
-                           moe_loss_enable=align_args.moe_loss_enable, **data_module)
+                           moe_loss_enable=align_args.moe_loss_enable, tokenizer=tokenizer, **data_module)
     resume = bool(glob.glob(os.path.join(training_args.output_dir, "checkpoint-*")))     # align_train.py:601-604
     trainer.train(resume_from_checkpoint=resume)
     model.config.use_cache = True

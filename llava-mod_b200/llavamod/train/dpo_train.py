@@ -52,13 +52,24 @@ def train(argv=None):
                                           dpo_args.ref_model_type, None, device)
     training_args.moe_enable = model_args.moe_enable
     path = (data_args.data_path or ["synthetic"])[0]
-    if not str(path).startswith("synthetic"):
-        raise NotImplementedError("LazyDPODataset (RLAIF-V JSON) is row N1 of SURVEY section 8f; use --data_path synthetic[:N]")
-    n = int(path.split(":")[1]) if ":" in path else 1024
     tower = model.get_image_tower()
-    ds = SyntheticDPODataset(n, training_args.model_max_length - tower.num_patches + 1, model.config.vocab_size, tower.config.image_size, training_args.seed)
+    if not str(path).startswith("synthetic"):
+        # RLAIF-V style preference JSON through the reference's lazy dataset + collator (data/dataset.py:253-517)
+        from ..data.dataset import make_dpo_data_module
+        from .align_train import load_tokenizer
+        tokenizer = load_tokenizer(model_args, training_args, dpo_args.policy_model_name_or_path)
+        model.config.pad_token_id = tokenizer.pad_token_id
+        data_args.image_processor = tower.image_processor
+        data_args.is_multimodal = True
+        data_module = make_dpo_data_module(tokenizer, data_args)
+    else:
+        tokenizer = None
+        n = int(path.split(":")[1]) if ":" in path else 1024
+        ds = SyntheticDPODataset(n, training_args.model_max_length - tower.num_patches + 1, model.config.vocab_size, tower.config.image_size,
+                                 training_args.seed)
+        data_module = dict(train_dataset=ds, eval_dataset=None, data_collator=collate_dpo)
     trainer = DPOTrainer(model=model, ref_model=ref_model, args=training_args, loss_type=dpo_args.loss_type,
-                         moe_loss_enable=dpo_args.moe_loss_enable, train_dataset=ds, data_collator=collate_dpo)
+                         moe_loss_enable=dpo_args.moe_loss_enable, tokenizer=tokenizer, **data_module)
     trainer.train(resume_from_checkpoint=bool(glob.glob(os.path.join(training_args.output_dir, "checkpoint-*"))))
     if not dist.is_initialized() or dist.get_rank() == 0:
         model.config.save_pretrained(training_args.output_dir)

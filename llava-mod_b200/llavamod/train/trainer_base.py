@@ -165,6 +165,15 @@ class BaseTrainer:
     # ---- loop ------------------------------------------------------------------------------------------------
     def get_train_dataloader(self):
         from torch.utils.data import DataLoader, DistributedSampler
+        if getattr(self.args, "group_by_modality_length", False) and hasattr(self.train_dataset, "modality_lengths"):
+            # reference: _get_train_sampler (align_trainer.py:311-322) -- global length-grouped order, then per-rank batches
+            from .sampler import LengthGroupedSampler, RankShard
+            a = self.args
+            grouped = LengthGroupedSampler(a.per_device_train_batch_size, world_size=self.world_size * a.gradient_accumulation_steps,
+                                           lengths=self.train_dataset.modality_lengths, group_by_modality=True)
+            sampler = RankShard(grouped, a.per_device_train_batch_size, self.rank, self.world_size)
+            return DataLoader(self.train_dataset, batch_size=a.per_device_train_batch_size, sampler=sampler, collate_fn=self.data_collator,
+                              num_workers=a.dataloader_num_workers, pin_memory=True, drop_last=True)
         sampler = DistributedSampler(self.train_dataset, shuffle=True, seed=self.args.seed) if self.world_size > 1 else None
         return DataLoader(self.train_dataset, batch_size=self.args.per_device_train_batch_size, sampler=sampler,
                           shuffle=(sampler is None), collate_fn=self.data_collator,

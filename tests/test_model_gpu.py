@@ -85,6 +85,39 @@ def test_qwen2_like_pair_gqa_teacher_with_wider_vocab(distill_all):
     torch.cuda.synchronize()
 
 
+def test_real_data_batch_through_trainer_matches_oracle(golden_dir):
+    """SURVEY 8f N1 end to end: records -> LazySupervisedDataset -> collator (tokeniser + CLIP processor; golden-checked against the
+    reference in tests/test_data_pipeline.py) -> AlignTrainer on the GPU, against the CPU oracle on the same batch.  The batch is ragged
+    on purpose: one image, two images, a text-only record (a blank image is fed and its features are consumed by an empty slice,
+    llava_arch.py:247-274) and an unreadable file (black fallback), right-padded to the longest sample."""
+    import types
+    from transformers import CLIPImageProcessor
+    from llavamod import conversation as conversation_lib
+    from llavamod.data import dataset as D
+    from tests.golden.make_data_golden import load_tokenizer
+    D.local_rank = 1
+    conversation_lib.set_default_conversation("qwen")
+    tok = load_tokenizer(os.path.join(golden_dir, "tiny_tokenizer.json"))
+    args = types.SimpleNamespace(image_folder=os.path.join(golden_dir, "data_imgs"), image_aspect_ratio="pad", is_multimodal=True,
+                                 image_processor=CLIPImageProcessor(size={"shortest_edge": 32}, crop_size={"height": 32, "width": 32}),
+                                 mm_use_im_start_end=False, num_frames=8, data_path=[os.path.join(golden_dir, "data_sft.json")])
+    mod = D.make_supervised_data_module(tok, args)
+    batch = mod["data_collator"]([mod["train_dataset"][i] for i in range(4)])
+    batch["images"] = [im.to(torch.bfloat16) for im in batch["images"]]
+    assert batch["input_ids"].shape == (4, 112) and len(batch["images"]) == 5 and not bool(batch["attention_mask"].all())
+    student, teacher = Hh.tiny_pair(vocab=424)            # >= len(tok) = 420, multiple of 8 (16-byte rows for the loss kernels)
+    student.config.pad_token_id = teacher.config.pad_token_id = tok.pad_token_id
+    Tn = 112 - 1 + 16                                      # longest spliced sample: record 0 (one image, 16 patches)
+    g = torch.Generator().manual_seed(11)
+    n_moe = sum(1 for l in student.model.layers if hasattr(l.mlp, "deepspeed_moe"))
+    noise = [R.gumbel_noise((4 * Tn, 4), g) for _ in range(n_moe)]
+    ref_loss, ref_m = Hh.oracle_mimic_loss(student, teacher, batch, noise, "kd_lm")
+    tr = Hh.make_trainer(student, teacher, "kd_lm")
+    loss, m = tr.compute_loss(student, dict(batch, moe_noise=[n.cuda() for n in noise]), return_outputs=True)
+    for k in ("loss", "loss/align", "loss/lm", "loss/moe_balance"):
+        assert abs(float(m[k]) - float(ref_m[k])) < 1e-2 * abs(float(ref_m[k])) + 1e-4, (k, float(m[k]), float(ref_m[k]))
+
+
 def test_padded_batch_goes_through_masked_attention():
     student, teacher = Hh.tiny_pair()
     batch, noise = Hh.tiny_batch(student, seed=2, pad=(0, 7))
