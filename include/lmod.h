@@ -121,6 +121,15 @@ int lmod_rmsnorm_fwd(const void* x, const void* res /* optional: x := x + res fi
                      float* rstd, void* stream);
 int lmod_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
                      int64_t rows, int64_t H, void* dx, void* stream);
+/* RMSNorm weight gradient (autograd of `self.weight * hidden_states.to(input_dtype)`, qwen1_5/modeling_qwen2.py:110):
+ * wgrad[h] += bf16( sum_r bf16(dy[r,h] * bf16(x[r,h] * rstd[r])) ).  x is the tensor the forward normalised (x_out of lmod_rmsnorm_fwd when a
+ * residual was fused), rstd its per-row output.  ws_zeroed: fp32 [H] workspace that must be zero on entry and is zero again on return.
+ * Only needed when the norm weights train (dense-student distillation, full SFT); the sparse recipes freeze them. */
+int lmod_rmsnorm_wgrad(const void* dy, const void* x, const float* rstd, int64_t rows, int64_t H, float* ws_zeroed, void* wgrad, void* stream);
+
+/* Token-embedding gradient behind the multimodal splice (nn.Embedding backward; llava_arch.py:262-274): for every row with src[row] >= 0,
+ * grad[src[row], :] += dout[row, :] (bf16 atomics; rows that hold image patches or padding carry src < 0, as in lmod_splice_embed). */
+int lmod_embed_grad(const void* dout, const int64_t* src, int64_t n_rows, int64_t H, void* grad, void* stream);
 int lmod_layernorm_fwd(const void* x, const void* w, const void* b, int64_t rows, int64_t H, float eps,
                        void* y, void* stream);
 /* rotate-half RoPE applied in place to q [rows, nh*hd] and k [rows, nkv*hd] (rows of a fused QKV buffer via ld).

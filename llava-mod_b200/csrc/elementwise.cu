@@ -261,6 +261,61 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(__nv_bfloat16* __restrict
   *p2 = pack8(o2);
 }
 
+// dW of RMSNorm: dw[h] += sum_rows bf16(dy[r,h] * xhat[r,h]),  xhat = bf16(x[r,h] * rstd[r])  (autograd of `weight * hidden_states.to(dtype)`,
+// modeling_qwen2.py:110; needed when the norms train: dense-student distillation / full SFT).  Grid (H/256 column slabs, row chunks);
+// a CTA keeps 8 column sums per thread over its rows, folds its 8 warps through shared memory and issues one fp32 red.add per column
+// into the [H] workspace; rmsnorm_wgrad_finish_kernel rounds once and accumulates into the bf16 gradient buffer.
+constexpr int NWG_ROWS_PER_CTA = 256;
+__global__ void __launch_bounds__(256) rmsnorm_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                           const float* __restrict__ rstd, int64_t rows, int H, float* __restrict__ ws) {
+  __shared__ float part[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = blockIdx.x * 32 + lane;                          // 16-byte vector (8 columns) of this thread
+  const int hv = H >> 3;
+  const int64_t r0 = (int64_t)blockIdx.y * NWG_ROWS_PER_CTA;
+  const int64_t r1 = min(rows, r0 + NWG_ROWS_PER_CTA);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (v < hv) {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      float d[8], xv[8];
+      unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(dy + r * H) + v), d);
+      unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(x + r * H) + v), xv);
+      const float rs = rstd[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += bf16_round(d[j] * bf16_round(xv[j] * rs));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;                                     // column within the 256-wide slab
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += part[w][c];
+  const int col = blockIdx.x * 256 + c;
+  if (col < H) atomicAdd(ws + col, t);
+}
+__global__ void rmsnorm_wgrad_finish_kernel(float* __restrict__ ws, int H, __nv_bfloat16* __restrict__ wgrad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H) return;
+  wgrad[i] = __float2bfloat16(__bfloat162float(wgrad[i]) + bf16_round(ws[i]));
+  ws[i] = 0.f;                                                   // the workspace is handed back zeroed
+}
+
+// dW of the token embedding (nn.Embedding backward behind the multimodal splice, llava_arch.py:262-274): every text row adds its
+// upstream gradient to the row of its token id; duplicates collide, hence bf16x2 atomics straight into the gradient buffer.
+__global__ void __launch_bounds__(256) embed_grad_kernel(const __nv_bfloat16* __restrict__ dout, const int64_t* __restrict__ src, int64_t n_rows,
+                                                        int H, __nv_bfloat16* __restrict__ grad) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const int64_t tok = src[row];
+  if (tok < 0) return;                                           // image-patch row or padding
+  const __nv_bfloat162* from = reinterpret_cast<const __nv_bfloat162*>(dout + row * H);
+  __nv_bfloat162* to = reinterpret_cast<__nv_bfloat162*>(grad + tok * H);
+  for (int i = lane; i < (H >> 1); i += 32) atomicAdd(to + i, from[i]);
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // out = bf16( bf16(silu(g)) * u ),  gate_up = [rows, 2I] (gate | up)
@@ -405,6 +460,22 @@ extern "C" int lmod_rmsnorm_bwd(const void* dy, const void* x, const void* w, co
   rmsnorm_bwd_kernel<<<(unsigned)rows, NORM_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                                (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,
                                                                                (int)H, (__nv_bfloat16*)dx);
+  LMOD_LAUNCH_OK();
+  return LMOD_OK;
+}
+extern "C" int lmod_rmsnorm_wgrad(const void* dy, const void* x, const float* rstd, int64_t rows, int64_t H, float* ws_zeroed, void* wgrad,
+                                  void* stream) {
+  LMOD_CHECK_ARG(dy && x && rstd && ws_zeroed && wgrad && rows > 0 && H > 0 && H % 8 == 0, "lmod_rmsnorm_wgrad: bad arguments (H %% 8 == 0 required)");
+  const dim3 grid((unsigned)((H + 255) / 256), (unsigned)((rows + NWG_ROWS_PER_CTA - 1) / NWG_ROWS_PER_CTA));
+  rmsnorm_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rstd, rows, (int)H, ws_zeroed);
+  LMOD_LAUNCH_OK();
+  rmsnorm_wgrad_finish_kernel<<<(unsigned)((H + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ws_zeroed, (int)H, (__nv_bfloat16*)wgrad);
+  LMOD_LAUNCH_OK();
+  return LMOD_OK;
+}
+extern "C" int lmod_embed_grad(const void* dout, const int64_t* src, int64_t n_rows, int64_t H, void* grad, void* stream) {
+  LMOD_CHECK_ARG(dout && src && grad && n_rows > 0 && H > 0 && H % 2 == 0, "lmod_embed_grad: bad arguments");
+  embed_grad_kernel<<<GRID1D(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, src, n_rows, (int)H, (__nv_bfloat16*)grad);
   LMOD_LAUNCH_OK();
   return LMOD_OK;
 }

@@ -222,7 +222,7 @@ class RMSNormFn(Function):
     (modeling_qwen2.py:796,808 / llava_qwen1_5_moe.py:156,167).  Returns (normed, residual_stream)."""
 
     @staticmethod
-    def forward(ctx, x, res, w, eps):
+    def forward(ctx, x, res, w, eps, wgrad=None):
         _need_cuda(x, w)
         x = _c(x)
         H = x.shape[-1]
@@ -238,6 +238,7 @@ class RMSNormFn(Function):
             call("lmod_rmsnorm_fwd", ptr(x), None, ptr(w), rows, H, eps, ptr(y), None, ptr(rstd))
         ctx.save_for_backward(s, w, rstd)
         ctx.had_res = res is not None
+        ctx.wgrad = wgrad                                   # view of the flat gradient buffer when the norm weight trains
         if res is None:
             return y, x.new_empty(0)
         return y, s
@@ -253,13 +254,26 @@ class RMSNormFn(Function):
             dsp = ptr(_c(ds))
         dx = torch.empty_like(s)
         call("lmod_rmsnorm_bwd", ptr(dy), ptr(s), ptr(w), ptr(rstd), dsp, rows, H, ptr(dx))
-        return dx, (dx if ctx.had_res else None), None, None
+        if ctx.wgrad is not None:
+            call("lmod_rmsnorm_wgrad", ptr(dy), ptr(s), ptr(rstd), rows, H, ptr(_zero_ws(s.device, H)), ptr(ctx.wgrad))
+        return dx, (dx if ctx.had_res else None), None, None, None
 
 
-def rmsnorm(x, w, eps, res=None):
+_ZERO_WS = {}
+
+
+def _zero_ws(device, n):
+    """fp32 workspace that kernels receive zeroed and hand back zeroed (lmod_rmsnorm_wgrad)."""
+    ws = _ZERO_WS.get(device)
+    if ws is None or ws.numel() < n:
+        ws = _ZERO_WS[device] = torch.zeros(max(n, 8192), dtype=torch.float32, device=device)
+    return ws
+
+
+def rmsnorm(x, w, eps, res=None, wgrad=None):
     """-> (y, stream) where stream = x + res (or x).  Without autograd the kernel is called directly."""
-    if torch.is_grad_enabled() and (x.requires_grad or (res is not None and res.requires_grad)):
-        y, s = RMSNormFn.apply(x, res, w, eps)
+    if torch.is_grad_enabled() and (x.requires_grad or (res is not None and res.requires_grad) or wgrad is not None):
+        y, s = RMSNormFn.apply(x, res, w, eps, wgrad)
         return y, (s if res is not None else x)
     x = _c(x)
     H = x.shape[-1]
@@ -396,7 +410,7 @@ def gelu(x):
 # ---------------------------------------------------------------------------------------------------
 class SpliceFn(Function):
     @staticmethod
-    def forward(ctx, feats, embed_w, src, img_index, n_patches):
+    def forward(ctx, feats, embed_w, src, img_index, n_patches, embed_grad=None):
         B, T = src.shape
         H = embed_w.shape[1]
         out = torch.empty(B, T, H, dtype=embed_w.dtype, device=embed_w.device)
@@ -405,6 +419,7 @@ class SpliceFn(Function):
         ctx.save_for_backward(src, img_index)
         ctx.fshape = feats.shape
         ctx.n_patches = n_patches
+        ctx.embed_grad = embed_grad                         # view of the flat gradient buffer when embed_tokens trains
         return out
 
     @staticmethod
@@ -412,14 +427,17 @@ class SpliceFn(Function):
         src, img_index = ctx.saved_tensors
         dfeats = torch.zeros(ctx.fshape, dtype=d.dtype, device=d.device)
         B, T = src.shape
-        call("lmod_splice_embed_bwd", ptr(_c(d)), ptr(src), ptr(img_index), B * T, d.shape[-1], ctx.n_patches, ptr(dfeats))
-        return dfeats, None, None, None, None
+        d = _c(d)
+        call("lmod_splice_embed_bwd", ptr(d), ptr(src), ptr(img_index), B * T, d.shape[-1], ctx.n_patches, ptr(dfeats))
+        if ctx.embed_grad is not None:
+            call("lmod_embed_grad", ptr(d), ptr(src), B * T, d.shape[-1], ptr(ctx.embed_grad))
+        return dfeats, None, None, None, None, None
 
 
-def splice_embed(feats, embed_w, src, img_index, n_patches):
+def splice_embed(feats, embed_w, src, img_index, n_patches, embed_grad=None):
     feats = _c(feats)
-    if torch.is_grad_enabled() and feats.requires_grad:
-        return SpliceFn.apply(feats, embed_w, src, img_index, n_patches)
+    if torch.is_grad_enabled() and (feats.requires_grad or embed_grad is not None):
+        return SpliceFn.apply(feats, embed_w, src, img_index, n_patches, embed_grad)
     B, T = src.shape
     H = embed_w.shape[1]
     out = torch.empty(B, T, H, dtype=embed_w.dtype, device=embed_w.device)

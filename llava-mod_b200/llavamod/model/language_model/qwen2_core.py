@@ -278,14 +278,15 @@ class Qwen2Model(nn.Module):
             at = layer.self_attn
             nh, nkv, hd = at.num_heads, at.num_key_value_heads, at.head_dim
             if branch is None:
-                x, stream = K.rmsnorm(stream, layer.input_layernorm.weight, cfg.rms_norm_eps)
+                x, stream = K.rmsnorm(stream, layer.input_layernorm.weight, cfg.rms_norm_eps, wgrad=self.gview(layer.input_layernorm.weight))
             else:
-                x, stream = K.rmsnorm(branch, layer.input_layernorm.weight, cfg.rms_norm_eps, res=stream)
+                x, stream = K.rmsnorm(branch, layer.input_layernorm.weight, cfg.rms_norm_eps, res=stream, wgrad=self.gview(layer.input_layernorm.weight))
             qkv = K.linear(x, at.qkv_weight, at.qkv_bias, self.gview(at.qkv_weight), self.gview(at.qkv_bias))
             qkv = K.rope_(qkv, cos, sin, pos, nh, nkv, hd)
             attn = _attention(qkv, B, T, nh, nkv, hd, mask4d)
             branch = K.linear(attn, at.o_proj.weight, None, self.gview(at.o_proj.weight), None)
-            x, stream = K.rmsnorm(branch, layer.post_attention_layernorm.weight, cfg.rms_norm_eps, res=stream)
+            x, stream = K.rmsnorm(branch, layer.post_attention_layernorm.weight, cfg.rms_norm_eps, res=stream,
+                                  wgrad=self.gview(layer.post_attention_layernorm.weight))
             mlp = layer.mlp
             if isinstance(mlp, MoE):
                 ds = mlp.deepspeed_moe
@@ -313,9 +314,9 @@ class Qwen2Model(nn.Module):
                     act = K.silu_mul(gu)
                 branch = K.linear(act, mlp.down_proj.weight, None, self.gview(mlp.down_proj.weight), None)
         if branch is None:
-            out, _ = K.rmsnorm(stream, self.norm.weight, cfg.rms_norm_eps)
+            out, _ = K.rmsnorm(stream, self.norm.weight, cfg.rms_norm_eps, wgrad=self.gview(self.norm.weight))
         else:
-            out, _ = K.rmsnorm(branch, self.norm.weight, cfg.rms_norm_eps, res=stream)
+            out, _ = K.rmsnorm(branch, self.norm.weight, cfg.rms_norm_eps, res=stream, wgrad=self.gview(self.norm.weight))
         return out.view(B, T, H), l_auxes, records
 
 

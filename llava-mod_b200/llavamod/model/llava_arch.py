@@ -176,7 +176,9 @@ class LlavaMetaForCausalLM(ABC):
         n_patches = feats.shape[1]
         if plan is None:   # host-side integer plan (a device tensor costs one sync, exactly like the reference's .sum()/.tolist())
             plan = self.make_splice_plan(input_ids, attention_mask, labels, n_patches, dev)
-        embeds = K.splice_embed(feats, self.get_model().embed_tokens.weight, plan["src"], plan["img"], n_patches)
+        core = self.get_model()
+        embeds = K.splice_embed(feats, core.embed_tokens.weight, plan["src"], plan["img"], n_patches,
+                                embed_grad=core.gview(core.embed_tokens.weight) if torch.is_grad_enabled() else None)
         if not plan["has_mask"]:
             new_mask = None
         else:       # "no padding" is known on the host, the decoder must not sync to find out

@@ -59,6 +59,12 @@ class TrainState:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
         dev = next(model.parameters()).device
+        # every trainable parameter must have a kernel that writes its gradient view: language-model linears / biases / norms / embeddings,
+        # lm_head, router wg, experts and the projector do; the CLIP tower is forward-only (frozen in every recipe of the reference)
+        orphans = [n for n, p in model.named_parameters() if p.requires_grad and "image_tower" in n]
+        if orphans:
+            raise NotImplementedError("trainable vision-tower parameters (%s ...): the tower's backward is not built -- the reference's "
+                                      "recipes keep it frozen" % orphans[0])
         u16, u32 = [], []
         for storage, members in _units(model):
             rg = [m.requires_grad for m in members]

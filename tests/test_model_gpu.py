@@ -154,6 +154,46 @@ def test_gradients_match_oracle_autograd():
     print("worst relative grad error", worst)
 
 
+def test_dense_student_full_parameter_gradients_match_oracle():
+    """Dense-to-dense distillation (shells/train/qwen/dense2dense_distillation.sh: --policy_model_type dense, only_kd): no MoE wrap, so
+    nothing is frozen by --train_modules and EVERY language-model parameter trains -- embeddings (through the splice), q/k/v biases,
+    attention weights, the three kinds of RMSNorm weights and lm_head, next to the FFN and the projector.  Gradients of all of them against
+    fp32 autograd of the oracle."""
+    from llavamod.model import synthetic as S
+    teacher = S.make_teacher(dict(S.ARCH["tiny"], intermediate_size=320), "tiny", seed=6)
+    student = S.make_teacher(dict(S.ARCH["tiny"]), "tiny", seed=7).train()
+    student.get_image_tower().load_state_dict(teacher.get_image_tower().state_dict())
+    for n, p in student.named_parameters():
+        p.requires_grad = "image_tower" not in n
+    batch, noise = Hh.tiny_batch(student, seed=8)
+    assert noise == []
+    sd_s = Hh.oracle_state(student)
+    names = [n for n, p in student.named_parameters() if p.requires_grad]
+    assert any("embed_tokens" in n for n in names) and any("input_layernorm" in n for n in names) and any("q_proj.bias" in n for n in names)
+    for k in names:
+        sd_s[k].requires_grad_(True)
+    ref_loss, _ = Hh.oracle_mimic_loss(student, teacher, batch, None, "only_kd", moe_loss_enable=False, sd_s=sd_s)
+    ref_loss.backward()
+    tr = Hh.make_trainer(student, teacher, "only_kd", moe_loss_enable=False)
+    opt = tr.create_optimizer()
+    opt.zero_grad()
+    loss = tr.compute_loss(student, dict(batch))
+    assert abs(float(loss) - float(ref_loss)) < 1e-2 * abs(float(ref_loss))
+    loss.backward()
+    torch.cuda.synchronize()
+    worst = ("", 0.0)
+    for n, p in student.named_parameters():
+        if not p.requires_grad:
+            continue
+        g, r = p.grad.float().cpu(), sd_s[n].grad
+        assert r is not None and r.norm().item() > 0, n
+        rel = (g - r).norm().item() / (r.norm().item() + 1e-12)
+        if rel > worst[1]:
+            worst = (n, rel)
+        assert rel < 0.08, (n, rel)
+    print("worst relative grad error", worst)
+
+
 def test_loss_curve_tracks_oracle_20_steps():
     """config 1 (2-layer/128-d student + teacher, 32x32 image): the GPU loss follows the fp32 CPU oracle step by step."""
     student, teacher = Hh.tiny_pair()
