@@ -132,6 +132,17 @@ class LlavaQwenForCausalLMBase(nn.Module, LlavaMetaForCausalLM):
             return None
         return self.router_aux_loss_coef * sum(l_auxes)                       # llava_qwen1_5_moe.py:431
 
+    def forward_train_loss(self, input_ids=None, attention_mask=None, labels=None, images=None, moe_noise=None, plan=None):
+        """Training-time `.loss` of `forward` without materialising the fp32 logits the reference returns (llava_qwen1_5_moe.py:408-434;
+        dense: modeling_qwen2.py:1195-1207): shifted CE (+ moe_loss).  -> (loss, ce.detach(), moe_loss or None)"""
+        r = self.forward_hidden(input_ids, attention_mask, None, None, labels, images, moe_noise, plan=plan)
+        hidden = r["hidden"]
+        B, T, H = hidden.shape
+        logits_lp = K.linear(hidden.reshape(B * T, H), self.lm_head.weight, None, self.lm_head_grad, None).view(B, T, -1)
+        ce = ShiftedCEFn.apply(logits_lp, r["labels"])
+        moe_loss = self.moe_loss_from(r["l_aux"]) if self.is_moe else None
+        return (ce if moe_loss is None else ce + moe_loss), ce.detach(), moe_loss
+
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
                 labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, images=None,
                 return_dict=None, moe_noise=None):

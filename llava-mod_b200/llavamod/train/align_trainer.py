@@ -219,26 +219,6 @@ class AlignTrainer(BaseTrainer):
                 return sig + ("pipelined",)
         return sig
 
-    def _fill_static(self, static, inputs):
-        images, plan = inputs["images"], inputs["splice_plan"]
-        if torch.is_tensor(images):
-            static["images"].copy_(images, non_blocking=True)
-        else:
-            for i, im in enumerate(images):
-                static["images"][i].copy_(im, non_blocking=True)
-        for k, v in plan.items():
-            if torch.is_tensor(v):
-                static["splice_plan"][k].copy_(v, non_blocking=True)
-
-    def _new_static(self, inputs):
-        dev = self.model.device
-        images, plan = inputs["images"], inputs["splice_plan"]
-        n = len(images) if not torch.is_tensor(images) else images.shape[0]
-        ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
-        return dict(input_ids=inputs["input_ids"], labels=inputs["labels"], attention_mask=inputs.get("attention_mask"),
-                    images=torch.empty((n,) + ish, dtype=self.model.dtype, device=dev),
-                    splice_plan={k: (torch.empty_like(v) if torch.is_tensor(v) else v) for k, v in plan.items()})
-
     def _graph_static_inputs(self, inputs, static, next_inputs=None, pipelined=False):
         if static is None:
             static = self._new_static(inputs)
