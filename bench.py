@@ -358,13 +358,15 @@ def run_ours(args):
     m_ce = torch.cat([lab[:, 1:] != -100, torch.zeros(lab.shape[0], 1, dtype=torch.bool)], 1)
     active = int((m_kd | m_ce).sum())
     kd_vocab = min(151936, V)
-    bytes_launch = active * 6 * kd_vocab + (T - active) * 2 * kd_vocab
+    compact = bool(getattr(trainer, "compact_head", False))
+    # compact head: the kernel only sees the supervised rows (6V B each); dense head: masked rows are zero-filled (2V B each)
+    bytes_launch = active * 6 * kd_vocab + (0 if compact else (T - active) * 2 * kd_vocab)
     ev = timers.get("kl_fwd_bwd", [])
     kl_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
     ach = bytes_launch / (kl_ms * 1e-3) / 1e9 if kl_ms > 0 else None
     prof = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "kl_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "kl_traffic_compact.json" if compact else "kl_traffic.json")) as f:
             prof = json.load(f)
     except Exception:
         pass
@@ -377,7 +379,8 @@ def run_ours(args):
                    "seq_len": T, "micro_batch": 1, "grad_accum": accum, "global_batch": accum * world, "loss": "kd_lm (mimic KL + LM + aux)",
                    "parallelism": "dp%d" % world, "l2": "working set per micro-batch (15.4 GB of teacher weights) >> 126 MB L2; no explicit flush",
                    "gemm": "hand-written tcgen05+TMA GEMM / grouped expert GEMM and tcgen05 flash-attention forward AND backward (liblmod_b200); no library GEMM or attention kernel on the path",
-                   "cuda_graphs": bool(trainer.use_cuda_graphs)},
+                   "cuda_graphs": bool(trainer.use_cuda_graphs),
+                   "loss_head": "supervised rows only (device-side row compaction, dynamic-extent GEMMs)" if bool(getattr(trainer, "compact_head", False)) else "all rows"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": 2 * accum * (img_bytes + plan_bytes), "d2h_bytes_per_step": 4,
                 "note": "each micro-batch uploads its own inputs and the look-ahead inputs of the next one (teacher runs one batch ahead)",
@@ -385,8 +388,10 @@ def run_ours(args):
         "roofline": {"kernel": "kl_fused_kernel (lmod_kl_fwd_bwd)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (ach / hbm_peak) if ach else None, "peak_source": src, "traffic": prof.get("traffic_bytes_per_launch"),
                      "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": kl_ms, "launches_timed": len(ev),
-                     "note": "%d of %d rows active (6V B each), masked rows zero-filled (2V B); survey-style 6V*N would read %.1f GB/s"
-                             % (active, T, (T * 6 * kd_vocab) / (kl_ms * 1e-3) / 1e9 if kl_ms > 0 else 0.0)},
+                     "note": ("%d of %d rows active (6V B each); " % (active, T))
+                             + ("the loss head runs on the active rows only (row compaction), masked rows cost nothing; "
+                                if compact else "masked rows zero-filled (2V B); ")
+                             + "survey-style 6V*N would read %.1f GB/s" % ((T * 6 * kd_vocab) / (kl_ms * 1e-3) / 1e9 if kl_ms > 0 else 0.0)},
         "step_tensor_util": ({"tflops_per_gpu": FLOP_PER_SAMPLE[wl_name] * value / world / 1e12, "peak_tflops": tf_peak,
                               "frac": FLOP_PER_SAMPLE[wl_name] * value / world / 1e12 / tf_peak} if wl_name in FLOP_PER_SAMPLE else None),
         "final_loss": final_loss,

@@ -51,6 +51,25 @@ int lmod_kl_fwd_bwd(const void* s_logits, int64_t ld_s, const void* t_logits, in
                     const int64_t* labels, int64_t n_rows, int64_t seq_len, int64_t vocab,
                     int distill_all, float w_kd, float w_ce, const float* counts2,
                     float* row_out, void* dlogits, int64_t ld_d, void* stream);
+/* Same over the batch's ACTIVE rows only (rows whose KD mask or CE mask is set; the reference computes every row and multiplies the rest
+ * by zero, align_trainer.py:512-526): s_logits / t_logits / dlogits hold row j = original row perm[j] for j < *count (device scalars from
+ * lmod_active_rows); labels and row_out stay indexed by the original row (row_out of inactive rows is not written and not read by
+ * lmod_kl_finalize).  perm == count == NULL: identical to lmod_kl_fwd_bwd. */
+int lmod_kl_fwd_bwd_rows(const void* s_logits, int64_t ld_s, const void* t_logits, int64_t ld_t,
+                         const int64_t* labels, int64_t n_rows, int64_t seq_len, int64_t vocab,
+                         int distill_all, float w_kd, float w_ce, const float* counts2,
+                         float* row_out, void* dlogits, int64_t ld_d, const int32_t* perm, const int32_t* count, void* stream);
+/* Active-row compaction for the loss head (csrc/rows.cu).  active(n) = labels[n] != -100 (or distill_all) || (n is not the last position of
+ * its sequence && labels[n+1] != -100) -- the union of the KD mask (align_trainer.py:512-515) and the shifted-CE mask
+ * (llava_qwen1_5_moe.py:413-421).  perm [n_rows] int32: perm[j] = original row of the j-th active row (ascending), -1 for j >= *count.
+ * gather: dst[j,:] = src[perm[j],:] for j < *count (perm NULL = identity), zeros for *count <= j < round_up(*count, pad_to), rows beyond
+ * untouched.  scatter: dst[perm[j],:] = src[j,:] for j < *count (dst zeroed by the caller).  All counts live in device memory: no host
+ * synchronisation, usable inside a captured CUDA graph. */
+int lmod_active_rows(const int64_t* labels, int64_t n_rows, int64_t seq_len, int distill_all, int32_t* perm, int32_t* count, void* stream);
+int lmod_gather_rows(const void* src, int64_t ld_src, const int32_t* perm, const int32_t* count, int64_t max_rows, int64_t cols,
+                     int64_t pad_to, void* dst, int64_t ld_dst, void* stream);
+int lmod_scatter_rows(const void* src, int64_t ld_src, const int32_t* perm, const int32_t* count, int64_t max_rows, int64_t cols,
+                      void* dst, int64_t ld_dst, void* stream);
 /* reduces row_out into {align_loss, ce_loss, n_kd, n_ce} (align = -sum m x / n_kd ; 0/0 -> NaN kept,
  * align_trainer.py:526) */
 int lmod_kl_finalize(const float* row_out, const int64_t* labels, int64_t n_rows, int64_t seq_len,
@@ -179,6 +198,13 @@ int lmod_adamw(float* master, float* m, float* v, const void* grad, int grad_is_
 int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, const void* bias, int epilogue,
                    float* d_f32_accum, void* stream);
+/* lmod_gemm_bf16 with extents read from DEVICE memory at kernel start (dense problems only): M_eff = min(M, *m_rows_dev),
+ * K_eff = min(K, round_up(*k_rows_dev, 64)); either pointer may be NULL (static extent).  Tensor maps and the launch grid are sized for the
+ * static M / K; tiles beyond the effective extent are skipped, an empty reduction contributes zero.  Rows of A (or of both MN-major
+ * operands, for a dynamic K) between the count and the next tile boundary must hold finite values (lmod_gather_rows zero-fills them). */
+int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                       void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, const void* bias, int epilogue,
+                       float* d_f32_accum, const int32_t* m_rows_dev, const int32_t* k_rows_dev, void* stream);
 int lmod_gemm_swiglu_ok(int64_t M, int64_t N);
 int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
                            const int32_t* offsets, int G, int64_t max_rows, int64_t M, int64_t N, int64_t K,

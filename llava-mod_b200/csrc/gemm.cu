@@ -47,7 +47,18 @@ struct GemmParams {
   int64_t b_group_rows;            // rows of B per group (N for K-major B) -- B coordinate offset
   int64_t d_group_stride;          // wgrad grouped: element stride of D per group
   int wgrad_grouped;               // 1: groups split the REDUCTION (K) range via offsets; M,N dense per group
+  // dense only: extents read from DEVICE memory at kernel start (the loss head works on the batch's supervised rows, whose count is
+  // data-dependent, inside a CUDA graph): M_eff = min(M, *m_dev), K_eff = min(K, round_up(*k_dev, BK)); null = static
+  const int32_t* m_dev;
+  const int32_t* k_dev;
 };
+
+__device__ __forceinline__ GemmParams effective_extents(const GemmParams& in) {
+  GemmParams p = in;
+  if (in.m_dev) p.M = min(in.M, max(0, *in.m_dev));
+  if (in.k_dev) p.K = min(in.K, (max(0, *in.k_dev) + BK - 1) / BK * BK);
+  return p;
+}
 
 // K-major 128B-swizzled tile (rows x 64 bf16, 128 B per row, 8-row atoms of 1024 B): LBO unused (=1), SBO = 1024; +32 B per UMMA_K
 // MN-major 128B-swizzled tile (64 k-rows x 64 mn per 8 KB block): LBO = 8192 (next 64-wide mn block), SBO = 1024 (next 8 k-rows);
@@ -109,7 +120,8 @@ __device__ __forceinline__ bool get_tile(const GemmParams& p, int t, Tile& o) {
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p_in) {
+  const GemmParams p = effective_extents(p_in);
   constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
@@ -277,7 +289,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {     // arriv
 
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p_in) {
+  const GemmParams p = effective_extents(p_in);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES2], empty_bar[STAGES2], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -409,7 +422,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           if (col >= p.N) break;
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
+          for (int j = 0; j < 8; ++j) f[j] = (num_k == 0) ? 0.f : __uint_as_float(r[v * 8 + j]);   // empty (dynamic) reduction: nothing was accumulated
           if (p.bias) {
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
             f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
@@ -503,8 +516,9 @@ int pick_bn(int64_t m_tiles, int64_t N) {
 // epilogue bit 0: D = bf16(D + acc) ;  d_f32_accum != null: fp32 D32 += acc (ldd applies to it) instead of the bf16 output;
 // epilogue bit 1: fused SwiGLU (B rows tile-interleaved [128 gate | 128 up] per 256; D has N/2 columns; CTA-pair kernel only);
 // epilogue bits 8..: split-K factor (fp32 atomic accumulation into D32, which the caller zero-initialises).
-extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
-                              int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum, void* stream) {
+extern "C" int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
+                                  int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum,
+                                  const int32_t* m_rows_dev, const int32_t* k_rows_dev, void* stream) {
   LMOD_CHECK_ARG(A && B && (D || d_f32_accum) && M > 0 && N > 0 && K > 0, "lmod_gemm_bf16: null pointer or empty problem");
   LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0 && N % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) &&
                  (!D || (uintptr_t)D % 16 == 0), "lmod_gemm_bf16: strides / N must be multiples of 8 elements and pointers 16-byte aligned (TMA)");
@@ -529,6 +543,7 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
     p2.M = (int)M; p2.N = (int)N; p2.K = (int)K; p2.beta = epilogue & 1; p2.splits = 1; p2.groups = 1; p2.bn = 256;
     p2.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
     p2.swiglu = (epilogue & 2) ? 1 : 0;
+    p2.m_dev = m_rows_dev; p2.k_dev = k_rows_dev;
     return dispatch2(a_mn_major != 0, b_mn_major != 0, ta, tb, p2, (cudaStream_t)stream);
   }
   const int BN = pick_bn(((M + BM - 1) / BM) * splits_req, N);
@@ -543,9 +558,15 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.beta = epilogue & 1; p.offsets = nullptr; p.groups = 1; p.bn = BN;
   p.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
   p.splits = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
+  p.m_dev = m_rows_dev; p.k_dev = k_rows_dev;
   LMOD_CHECK_ARG(p.splits == 1 || d_f32_accum, "lmod_gemm_bf16: split-K needs the fp32 accumulate output");
   const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN)) * p.splits;
   return dispatch(a_mn_major != 0, b_mn_major != 0, ta, tb, p, tiles, (cudaStream_t)stream);
+}
+
+extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
+                              int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum, void* stream) {
+  return lmod_gemm_bf16_dyn(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, M, N, K, bias, epilogue, d_f32_accum, nullptr, nullptr, stream);
 }
 
 // 1 when lmod_gemm_bf16 would run this problem on the CTA-pair kernel (which is the one that offers the fused SwiGLU epilogue)

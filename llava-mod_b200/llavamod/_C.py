@@ -21,6 +21,10 @@ _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 SIGNATURES = {
     "lmod_kl_counts": [_P, _L, _L, _I, _P, _P],
     "lmod_kl_fwd_bwd": [_P, _L, _P, _L, _P, _L, _L, _L, _I, _F, _F, _P, _P, _P, _L, _P],
+    "lmod_kl_fwd_bwd_rows": [_P, _L, _P, _L, _P, _L, _L, _L, _I, _F, _F, _P, _P, _P, _L, _P, _P, _P],
+    "lmod_active_rows": [_P, _L, _L, _I, _P, _P, _P],
+    "lmod_gather_rows": [_P, _L, _P, _P, _L, _L, _L, _P, _L, _P],
+    "lmod_scatter_rows": [_P, _L, _P, _P, _L, _L, _P, _L, _P],
     "lmod_kl_finalize": [_P, _P, _L, _L, _I, _P, _P],
     "lmod_logp_gather_fwd": [_P, _L, _P, _L, _L, _L, _P, _P, _P, _I, _P],
     "lmod_logp_gather_bwd": [_P, _L, _P, _L, _L, _L, _P, _P, _I, _P, _L, _P],
@@ -49,6 +53,7 @@ SIGNATURES = {
     "lmod_sumsq": [_P, _I, _L, _P, _P],
     "lmod_adamw": [_P, _P, _P, _P, _I, _P, _L, _F, _F, _F, _F, _F, _L, _P, _F, _F, _P],
     "lmod_gemm_bf16": [_P, _L, _I, _P, _L, _I, _P, _L, _L, _L, _L, _P, _I, _P, _P],
+    "lmod_gemm_bf16_dyn": [_P, _L, _I, _P, _L, _I, _P, _L, _L, _L, _L, _P, _I, _P, _P, _P, _P],
     "lmod_gemm_swiglu_ok": [_L, _L],
     "lmod_grouped_gemm_bf16": [_P, _L, _P, _L, _P, _L, _P, _I, _L, _L, _L, _L, _I, _I, _P],
     "lmod_attn_fwd": [_P, _L, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P],

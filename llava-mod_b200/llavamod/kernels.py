@@ -37,7 +37,7 @@ def mm_nt(x, w, bias=None):
     return y if x.dim() == 2 else y.view(*x.shape[:-1], w.shape[0])     # no view object for the 2-D case (RoPE writes in place)
 
 
-def mm_nn(dy, w):
+def mm_nn(dy, w, m_dev=None):
     """dx[M,K] = dy[M,N] @ w[N,K] -- nn.Linear dgrad: B operand = w as stored (MN-major), no transpose copy.
     Few output tiles + a very long reduction (lm_head dgrad: K = vocab) -> split-K with fp32 atomics."""
     dy2 = _rows(dy)
@@ -47,34 +47,69 @@ def mm_nn(dy, w):
     if tiles < 100 and N >= 16384:
         split = max(2, min(16, 148 // max(1, tiles)))
         acc = torch.zeros(M, Kout, dtype=torch.float32, device=dy.device)
-        gemm(dy2, w, b_mn=True, out_f32=acc, split_k=split)
+        gemm(dy2, w, b_mn=True, out_f32=acc, split_k=split, m_dev=m_dev)
         return acc.to(dy.dtype)
+    if m_dev is not None:
+        out = torch.zeros(M, Kout, dtype=dy.dtype, device=dy.device)         # rows past the dynamic extent stay zero
+        return gemm(dy2, w, b_mn=True, out=out, m_dev=m_dev)
     return gemm(dy2, w, b_mn=True)
 
 
-def mm_tn_acc(dy, x, grad):
+def mm_tn_acc(dy, x, grad, k_dev=None):
     """grad[N,K] += dy[M,N]^T @ x[M,K] -- nn.Linear wgrad accumulated in place into the flat grad buffer (both operands MN-major)."""
     dy2, x2 = _rows(dy), _rows(x)
     if grad.dtype == torch.float32:
-        gemm(dy2, x2, a_mn=True, b_mn=True, out_f32=grad)
+        gemm(dy2, x2, a_mn=True, b_mn=True, out_f32=grad, k_dev=k_dev)
     else:
-        gemm(dy2, x2, a_mn=True, b_mn=True, out=grad, accumulate=True)
+        gemm(dy2, x2, a_mn=True, b_mn=True, out=grad, accumulate=True, k_dev=k_dev)
 
 
-def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, out_f32=None, split_k=1):
+# ---- active-row compaction of the loss head (csrc/rows.cu) ---------------------------------------------------------------------
+ROW_PAD = 256            # GEMM tile height: gathered buffers are zero-filled up to the next multiple so partial tiles stay exact zeros
+
+
+def active_rows(labels_flat, seq_len, distill_all=False):
+    """-> (perm int32 [N], count int32 [1]) on the device; no host sync."""
+    _need_cuda(labels_flat)
+    n = labels_flat.numel()
+    perm = torch.empty(n, dtype=torch.int32, device=labels_flat.device)
+    count = torch.empty(1, dtype=torch.int32, device=labels_flat.device)
+    call("lmod_active_rows", ptr(labels_flat), n, seq_len, 1 if distill_all else 0, ptr(perm), ptr(count))
+    return perm, count
+
+
+def gather_rows(x2, perm, count, out=None):
+    """Compact copy [round_up(N, ROW_PAD), H] of the rows perm[:count] of x2 (perm None: the first count rows); pad rows zeroed."""
+    n, h = x2.shape
+    if out is None:
+        out = torch.empty((n + ROW_PAD - 1) // ROW_PAD * ROW_PAD, h, dtype=x2.dtype, device=x2.device)
+    call("lmod_gather_rows", ptr(x2), x2.stride(0), ptr(perm) if perm is not None else None, ptr(count), out.shape[0], h, ROW_PAD,
+         ptr(out), out.stride(0))
+    return out
+
+
+def scatter_rows(xc, perm, count, n):
+    out = torch.zeros(n, xc.shape[1], dtype=xc.dtype, device=xc.device)
+    call("lmod_scatter_rows", ptr(xc), xc.stride(0), ptr(perm), ptr(count), min(xc.shape[0], n), xc.shape[1], ptr(out), out.stride(0))
+    return out
+
+
+def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, out_f32=None, split_k=1, m_dev=None, k_dev=None):
     """Hand-written tcgen05/TMA GEMM (lmod_gemm_bf16).  D[M,N] (+)= A * B^T with
-       a_mn=False: a is [M,K] ; True: a is [K,M]     b_mn=False: b is [N,K] ; True: b is [K,N]."""
+       a_mn=False: a is [M,K] ; True: a is [K,M]     b_mn=False: b is [N,K] ; True: b is [K,N].
+       m_dev / k_dev: int32 device scalars bounding the rows of D / the reduction (lmod_gemm_bf16_dyn; active-row loss head)."""
     _need_cuda(a, b)
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N = b.shape[1] if b_mn else b.shape[0]
+    dyn = (ptr(m_dev) if m_dev is not None else None, ptr(k_dev) if k_dev is not None else None)
     if out_f32 is not None:
-        call("lmod_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), None, out_f32.stride(0), M, N, K, None,
-             (int(split_k) << 8) if split_k > 1 else 0, ptr(out_f32))
+        call("lmod_gemm_bf16_dyn", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), None, out_f32.stride(0), M, N, K, None,
+             (int(split_k) << 8) if split_k > 1 else 0, ptr(out_f32), *dyn)
         return out_f32
     if out is None:
         out = torch.empty(M, N, dtype=a.dtype, device=a.device)
-    call("lmod_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0), M, N, K,
-         ptr(bias) if bias is not None else None, 1 if accumulate else 0, None)
+    call("lmod_gemm_bf16_dyn", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0), M, N, K,
+         ptr(bias) if bias is not None else None, 1 if accumulate else 0, None, *dyn)
     return out
 
 
@@ -592,9 +627,10 @@ class _Timed:
             TIMERS.setdefault(self.name, []).append((self.a, self.b))
 
 
-def kl_fused(s_logits, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all=False, dlogits=None):
+def kl_fused(s_logits, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all=False, dlogits=None, rows=None):
     """Raw kernel call.  s_logits/t_logits [N,ld] bf16, labels [N] int64.  Returns (out4, row_out).
-    out4 = {align_loss, ce_loss, n_kd, n_ce}.  dlogits (may alias s_logits) receives the gradient."""
+    out4 = {align_loss, ce_loss, n_kd, n_ce}.  dlogits (may alias s_logits) receives the gradient.
+    rows = (perm, count) from active_rows(): the logits buffers hold only the active rows, compacted."""
     _need_cuda(s_logits, t_logits, labels)
     N = labels.numel()
     dev = s_logits.device
@@ -604,9 +640,10 @@ def kl_fused(s_logits, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all
     da = 1 if distill_all else 0
     call("lmod_kl_counts", ptr(labels), N, seq_len, da, ptr(counts))
     with _Timed("kl_fwd_bwd"):
-        call("lmod_kl_fwd_bwd", ptr(s_logits), s_logits.stride(0), ptr(t_logits), t_logits.stride(0), ptr(labels), N, seq_len, vocab, da,
+        call("lmod_kl_fwd_bwd_rows", ptr(s_logits), s_logits.stride(0), ptr(t_logits), t_logits.stride(0), ptr(labels), N, seq_len, vocab, da,
              float(w_kd), float(w_ce), ptr(counts), ptr(row_out), ptr(dlogits) if dlogits is not None else None,
-             dlogits.stride(0) if dlogits is not None else 0)
+             dlogits.stride(0) if dlogits is not None else 0, ptr(rows[0]) if rows is not None else None,
+             ptr(rows[1]) if rows is not None else None)
     call("lmod_kl_finalize", ptr(row_out), ptr(labels), N, seq_len, da, ptr(out4))
     return out4, row_out
 
@@ -617,15 +654,18 @@ class DistillHeadFn(Function):
     sweep over the vocabulary.  Returns (w_kd*align + w_ce*ce, align, ce); only the first is differentiable."""
 
     @staticmethod
-    def forward(ctx, hidden, w_head, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all, head_grad):
+    def forward(ctx, hidden, w_head, t_logits, labels, seq_len, vocab, w_kd, w_ce, distill_all, head_grad, perm, count):
         h2 = _c(hidden).reshape(-1, hidden.shape[-1])
-        logits = mm_nt(h2, w_head)                                      # [N, Vs] bf16
+        rows = (perm, count) if perm is not None else None
+        if rows is not None:
+            h2 = gather_rows(h2, perm, count)                             # active rows only; t_logits is compact the same way
+        logits = gemm(h2, w_head, m_dev=count)                            # [N(+pad), Vs] bf16
         if logits.shape[1] != vocab and w_ce != 0.0:
             raise _C.LmodError("fused CE needs student vocab == kd vocab slice")
-        out4, _ = kl_fused(logits, t_logits, labels.reshape(-1), seq_len, vocab, w_kd, w_ce, distill_all, dlogits=logits)
+        out4, _ = kl_fused(logits, t_logits, labels.reshape(-1), seq_len, vocab, w_kd, w_ce, distill_all, dlogits=logits, rows=rows)
         if logits.shape[1] > vocab:
             logits[:, vocab:].zero_()
-        ctx.save_for_backward(logits, w_head, h2)
+        ctx.save_for_backward(logits, w_head, h2, perm, count)
         ctx.hshape = hidden.shape
         ctx.head_grad = head_grad
         align, ce = out4[0], out4[1]
@@ -635,18 +675,27 @@ class DistillHeadFn(Function):
 
     @staticmethod
     def backward(ctx, g, _a, _c2):
-        dlogits, w_head, h2 = ctx.saved_tensors
-        dh = mm_nn(dlogits, w_head)
-        dh = (dh * g.to(dh.dtype)).reshape(ctx.hshape)
+        dlogits, w_head, h2, perm, count = ctx.saved_tensors
+        # the kernel produced d(total)/d(logits); the upstream scalar g multiplies the two SMALL operands instead of the [N,V] / [V,H] results:
+        # dH = g * (dlogits @ W),  dW += dlogits^T @ (g * h)
+        gs = g.to(h2.dtype)
+        dh = mm_nn(dlogits, w_head, m_dev=count) * gs
+        if perm is not None:
+            n = 1
+            for d in ctx.hshape[:-1]:
+                n *= d
+            dh = scatter_rows(dh, perm, count, n)
+        dh = dh.reshape(ctx.hshape)
         if ctx.head_grad is not None:
-            tmp = torch.zeros_like(ctx.head_grad)
-            mm_tn_acc(dlogits, h2, tmp)
-            ctx.head_grad.add_(tmp * g.to(tmp.dtype))
-        return dh, None, None, None, None, None, None, None, None, None
+            mm_tn_acc(dlogits, h2 * gs, ctx.head_grad, k_dev=count)
+        return dh, None, None, None, None, None, None, None, None, None, None, None
 
 
-def distill_head(hidden, w_head, t_logits, labels, vocab, w_kd, w_ce, distill_all=False, head_grad=None):
-    return DistillHeadFn.apply(hidden, w_head, t_logits, labels, labels.shape[-1], vocab, float(w_kd), float(w_ce), bool(distill_all), head_grad)
+def distill_head(hidden, w_head, t_logits, labels, vocab, w_kd, w_ce, distill_all=False, head_grad=None, rows=None):
+    """rows = (perm, count) from active_rows(labels): t_logits then holds the teacher logits of the active rows only (compact)."""
+    perm, count = rows if rows is not None else (None, None)
+    return DistillHeadFn.apply(hidden, w_head, t_logits, labels, labels.shape[-1], vocab, float(w_kd), float(w_ce), bool(distill_all), head_grad,
+                               perm, count)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -81,6 +81,9 @@ class AlignTrainer(BaseTrainer):
         self.overlap_teacher = bool(int(os.environ.get("LLAVAMOD_OVERLAP_TEACHER", "1"))) and next(model.parameters()).is_cuda
         self._teacher_stream = torch.cuda.Stream() if self.overlap_teacher else None
         self.pipeline_teacher = bool(int(os.environ.get("LLAVAMOD_PIPELINE_TEACHER", "1")))
+        # loss head on the batch's supervised rows only (csrc/rows.cu): both lm_head GEMMs, the fused KL+CE kernel and the lm_head
+        # backward skip the positions the reference multiplies by zero
+        self.compact_head = bool(int(os.environ.get("LLAVAMOD_COMPACT_HEAD", "1")))
 
     # ---- API-compat pieces (materialising forms, our kernels) ------------------------------------------------
     def _moe_loss_of(self, outputs):
@@ -119,11 +122,19 @@ class AlignTrainer(BaseTrainer):
         return torch.stack([im.to(dev, non_blocking=True) for im in images]) if not torch.is_tensor(images) else images.to(dev)
 
     def _teacher_forward(self, fwd, tower_feats, plan):
-        """Frozen teacher -> bf16 logits [N, Vt] (get_p's forward, align_trainer.py:458-461; its softmax lives in the fused kernel)."""
+        """Frozen teacher -> bf16 logits (get_p's forward, align_trainer.py:458-461; its softmax lives in the fused kernel).
+        -> (logits, (B, T'), rows): with the compact head `rows` = (perm, count) of the supervised rows of the post-splice labels and
+        logits[j] belongs to row perm[j]; otherwise rows is None and logits is [B*T', Vt]."""
         ref = self.ref_model.module
         t = ref.forward_hidden(**fwd, tower_features=tower_feats, plan=plan)
         th = t["hidden"]
-        return K.mm_nt(th.reshape(-1, th.shape[-1]), ref.lm_head.weight), th.shape[:2]
+        h2 = th.reshape(-1, th.shape[-1])
+        rows = None
+        if self.compact_head and t["labels"] is not None:
+            lab = t["labels"]
+            rows = K.active_rows(lab.reshape(-1), lab.shape[-1], bool(getattr(self.args, "distill_all_tokens", False)))
+            h2 = K.gather_rows(h2, *rows)
+        return K.gemm(h2, ref.lm_head.weight, m_dev=rows[1] if rows is not None else None), th.shape[:2], rows
 
     def compute_loss(self, model, inputs: Dict[str, Union[torch.Tensor, Any]], return_outputs=False):
         assert self.ref_model is not None, "ref model can not be none!"
@@ -155,22 +166,25 @@ class AlignTrainer(BaseTrainer):
             if pipe is not None:
                 nxt = pipe["next"]
                 tower_next = model.get_image_tower()(nxt["images"].to(model.dtype))
-                t_next, _ = self._teacher_forward(dict(input_ids=nxt["input_ids"], labels=nxt["labels"], attention_mask=nxt.get("attention_mask"),
-                                                       images=nxt["images"]), tower_next, nxt["splice_plan"])
-                t_logits, t_shape = pipe["t_cur"], pipe["t_shape"]
+                t_next, _, rows_next = self._teacher_forward(dict(input_ids=nxt["input_ids"], labels=nxt["labels"],
+                                                                  attention_mask=nxt.get("attention_mask"), images=nxt["images"]),
+                                                             tower_next, nxt["splice_plan"])
+                t_logits, t_shape, rows = pipe["t_cur"], pipe["t_shape"], pipe["rows_cur"]
             else:
-                t_logits, t_shape = self._teacher_forward(fwd, tower_feats, plan)
+                t_logits, t_shape, rows = self._teacher_forward(fwd, tower_feats, plan)
         s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"), plan=plan)
         if side is not None and pipe is None:
             main.wait_stream(side)
             t_logits.record_stream(main)
+            for r in (rows or ()):
+                r.record_stream(main)
         labels = s["labels"]
         if s["hidden"].shape[:2] != labels.shape or tuple(t_shape) != tuple(labels.shape):
             raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
         vocab = min(self.kd_vocab, model.config.vocab_size, t_logits.shape[-1])
         w_ce = 0.0 if self.loss_type == "only_kd" else 1.0
         total, align_loss, ce = K.distill_head(s["hidden"], model.lm_head.weight, t_logits, labels, vocab, 1.0, w_ce,
-                                               bool(getattr(self.args, "distill_all_tokens", False)), model.lm_head_grad)
+                                               bool(getattr(self.args, "distill_all_tokens", False)), model.lm_head_grad, rows=rows)
         model_moe_loss = model.moe_loss_from(s["l_aux"]) if getattr(model, "is_moe", False) else None
         # model.loss = CE (+ moe_loss)   llava_qwen1_5_moe.py:421,434
         policy_sft_loss = ce if model_moe_loss is None else ce + model_moe_loss.detach()
@@ -187,7 +201,7 @@ class AlignTrainer(BaseTrainer):
                    "loss/moe_balance": moe_loss.detach().mean(), "loss/lm": policy_sft_loss.detach().mean()}
         self.store_metrics(outputs, train_eval="train")
         if pipe is not None:
-            pipe["t_next"], pipe["tower_next"] = t_next, tower_next      # copied into the "current" buffers after the backward
+            pipe["t_next"], pipe["tower_next"], pipe["rows_next"] = t_next, tower_next, rows_next   # -> "current" buffers after the backward
         if return_outputs:
             return losses.mean(), outputs
         return losses.mean()
@@ -228,20 +242,24 @@ class AlignTrainer(BaseTrainer):
                 with torch.no_grad():
                     self._fill_static(nxt, inputs)
                     tower = self.model.get_image_tower()(nxt["images"].to(self.model.dtype))
-                    t_cur, t_shape = self._teacher_forward(dict(input_ids=inputs["input_ids"], labels=inputs["labels"],
-                                                                attention_mask=inputs.get("attention_mask"), images=nxt["images"]),
-                                                           tower, nxt["splice_plan"])
-                static["_pipeline"] = dict(next=nxt, t_cur=t_cur.clone(), tower_cur=tower.clone(), t_shape=tuple(t_shape), holds=inputs)
+                    t_cur, t_shape, rows_cur = self._teacher_forward(dict(input_ids=inputs["input_ids"], labels=inputs["labels"],
+                                                                          attention_mask=inputs.get("attention_mask"), images=nxt["images"]),
+                                                                     tower, nxt["splice_plan"])
+                static["_pipeline"] = dict(next=nxt, t_cur=t_cur.clone(), tower_cur=tower.clone(), t_shape=tuple(t_shape), holds=inputs,
+                                           rows_cur=tuple(r.clone() for r in rows_cur) if rows_cur is not None else None)
         self._fill_static(static, inputs)
         if pipelined:
             pipe = static["_pipeline"]
             if pipe["holds"] is not inputs:       # the "current" buffers do not belong to this batch (first call / caller skipped ahead)
                 with torch.no_grad():
                     tower = self.model.get_image_tower()(static["images"].to(self.model.dtype))
-                    t_cur, _ = self._teacher_forward(dict(input_ids=inputs["input_ids"], labels=inputs["labels"],
-                                                          attention_mask=inputs.get("attention_mask"), images=static["images"]),
-                                                     tower, static["splice_plan"])
+                    t_cur, _, rows_cur = self._teacher_forward(dict(input_ids=inputs["input_ids"], labels=inputs["labels"],
+                                                                    attention_mask=inputs.get("attention_mask"), images=static["images"]),
+                                                               tower, static["splice_plan"])
                     pipe["t_cur"].copy_(t_cur)
+                    if rows_cur is not None:
+                        for dst, src in zip(pipe["rows_cur"], rows_cur):
+                            dst.copy_(src)
                     pipe["tower_cur"].copy_(tower)
             self._fill_static(pipe["next"], next_inputs)
             pipe["holds"] = next_inputs           # after this replay the "current" buffers describe next_inputs
@@ -253,7 +271,13 @@ class AlignTrainer(BaseTrainer):
         if pipe is not None:
             main = torch.cuda.current_stream()
             main.wait_stream(self._teacher_stream)
-            pipe["t_cur"].copy_(pipe["t_next"])
+            if pipe.get("rows_cur") is not None:
+                # hand over only the supervised rows of the next batch's teacher logits (+ their index list), not the whole [N, Vt] buffer
+                K.gather_rows(pipe["t_next"], None, pipe["rows_next"][1], out=pipe["t_cur"])
+                for dst, src in zip(pipe["rows_cur"], pipe["rows_next"]):
+                    dst.copy_(src)
+            else:
+                pipe["t_cur"].copy_(pipe["t_next"])
             pipe["tower_cur"].copy_(pipe["tower_next"])
 
     def log(self, logs: Dict[str, float]) -> None:

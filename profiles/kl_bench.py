@@ -13,16 +13,23 @@ for frac, tag in ((0.0, "all rows active"), (0.4, "40% masked head"), (0.57, "be
     labels[: int(frac * T)] = -100
     active = int(((labels != -100) | torch.cat([labels[1:] != -100, torch.zeros(1, dtype=torch.bool, device=dev)])).sum())
     by = active * 6 * V + (T - active) * 2 * V
-    d = torch.empty_like(s)
+    compact = os.environ.get("COMPACT", "1") == "1"
+    if compact:                      # what the trainer does: the kernel only sees the supervised rows
+        rows = K.active_rows(labels, T)
+        s_in, t_in = K.gather_rows(s, *rows), K.gather_rows(t, *rows)
+        by = active * 6 * V
+    else:
+        rows, s_in, t_in = None, s, t
+    d = torch.empty_like(s_in)
     for _ in range(3):
-        K.kl_fused(s, t, labels, T, V, 1.0, 1.0, False, dlogits=d)
+        K.kl_fused(s_in, t_in, labels, T, V, 1.0, 1.0, False, dlogits=d, rows=rows)
     ts = []
     for _ in range(10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); K.kl_fused(s, t, labels, T, V, 1.0, 1.0, False, dlogits=d); e1.record()
+        e0.record(); K.kl_fused(s_in, t_in, labels, T, V, 1.0, 1.0, False, dlogits=d, rows=rows); e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     ms = ts[len(ts) // 2]
-    print("%-8s %-32s %.3f ms  %.0f GB/s (whole kl_fused call: counts + fused + finalize)" % (os.environ.get("LMOD_KL_MODE", "default"), tag, ms, by / ms / 1e6), flush=True)
+    print("%-8s %-7s %-32s %.3f ms  %.0f GB/s (whole kl_fused call: counts + fused + finalize)" % (os.environ.get("LMOD_KL_MODE", "default"), "compact" if compact else "dense", tag, ms, by / ms / 1e6), flush=True)
