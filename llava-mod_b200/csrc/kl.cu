@@ -24,7 +24,7 @@ namespace {
 constexpr int KL_CHUNKS = 4;       // mbarrier-tracked load chunks per slice
 constexpr int KL_MAX_CS = 8;
 constexpr int KL_MIN_CTAS = 2;       // two CTAs per SM (2 x 76 KB of shared memory)
-constexpr int KL_DEFAULT_MODE = 0;      // measured (profiles/kl_modes_r1.txt): sb256 0.67 ms, db256 1.10 ms, db512 1.24 ms (all rows active)
+constexpr int KL_DEFAULT_MODE = 5;      // sb128.  measured (profiles/kl_modes_r1.txt, all rows active): sb128 0.60 ms, sb256 0.64, sb384 0.72, sb512 0.90, db256 1.10, db512 1.24
 
 struct KlParams {
   const __nv_bfloat16* s;
@@ -430,9 +430,13 @@ extern "C" int lmod_kl_fwd_bwd_rows(const void* s_logits, int64_t ld_s, const vo
 
   // LMOD_KL_MODE: "sb256" one slice buffer, 2 CTAs/SM (round-1 first version); "db256"/"db512" double-buffered slice, 1 CTA/SM
   static const char* mode_env = getenv("LMOD_KL_MODE");
-  static const int mode = !mode_env ? KL_DEFAULT_MODE : (!strcmp(mode_env, "sb256") ? 0 : (!strcmp(mode_env, "db256") ? 1 : 2));
+  static const int mode = !mode_env ? KL_DEFAULT_MODE
+                          : (!strcmp(mode_env, "sb256") ? 0 : (!strcmp(mode_env, "db256") ? 1 : (!strcmp(mode_env, "sb512") ? 3 : (!strcmp(mode_env, "sb384") ? 4 : (!strcmp(mode_env, "sb128") ? 5 : 2)))));
   const bool db_fits = smem * 2 <= 220 * 1024;
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 3) return kl_launch<512, 1>(p, cs, smem, n_rows, st);
+  if (mode == 4) return kl_launch<384, 1>(p, cs, smem, n_rows, st);
+  if (mode == 5) return kl_launch<128, 1>(p, cs, smem, n_rows, st);
   if (mode == 0 || !db_fits) return kl_launch<256, 1>(p, cs, smem, n_rows, st);
   return (mode == 1) ? kl_launch<256, 2>(p, cs, smem, n_rows, st) : kl_launch<512, 2>(p, cs, smem, n_rows, st);
 }
