@@ -8,7 +8,8 @@ import sys
 
 def classify(name):
     own = ("kl_", "logp_", "moe_", "rmsnorm", "layernorm", "rope_kernel", "silu_mul", "bias_act", "gelu_bwd", "add_kernel", "splice_",
-           "sumsq", "adamw", "softmax_rows", "align_dense", "lmod_gemm", "lmod_attn")
+           "sumsq", "adamw", "softmax_rows", "align_dense", "lmod_gemm", "lmod_attn", "gemm_tcgen05", "gemm2_tcgen05", "attn_fwd", "attn_bwd",
+           "attn_dsum", "attn_dq", "rope_vec", "active_rows", "gather_rows", "scatter_rows", "embed_grad", "rmsnorm_wgrad")
     if any(o in name for o in own):
         return "ours"
     if "flash" in name.lower() or "fmha" in name.lower():
