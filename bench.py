@@ -248,10 +248,20 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # the one JSON line is all rank 0 may print on stdout: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the one JSON line is all rank 0 may print on stdout, but NCCL printf()s its "NCCL version ..." banner there whenever NCCL_DEBUG is
+        # VERSION / WARN / INFO: send the C-level stdout to stderr while the communicator comes up (init + first collective)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local)
     wl_name = args.workload
     wl = WORKLOADS[wl_name]

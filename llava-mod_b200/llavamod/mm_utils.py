@@ -47,3 +47,35 @@ def tokenizer_image_token(prompt, tokenizer, image_token_index=IMAGE_TOKEN_INDEX
 def get_model_name_from_path(model_path):
     parts = model_path.strip("/").split("/")
     return parts[-2] + "_" + parts[-1] if parts[-1].startswith("checkpoint-") else parts[-1]
+
+
+class KeywordsStoppingCriteria:
+    """Stop when the newly generated tail decodes to (or ends with the ids of) one of `keywords` (mm_utils.py:73-105; a plain callable
+    `(output_ids, scores) -> bool`, which is all `generate` needs -- no dependency on transformers.StoppingCriteria)."""
+
+    def __init__(self, keywords, tokenizer, input_ids):
+        self.keywords = keywords
+        self.keyword_ids = []
+        self.max_keyword_len = 0
+        for kw in keywords:
+            ids = tokenizer(kw).input_ids
+            if len(ids) > 1 and ids[0] == getattr(tokenizer, "bos_token_id", None):
+                ids = ids[1:]
+            self.max_keyword_len = max(self.max_keyword_len, len(ids))
+            self.keyword_ids.append(torch.tensor(ids))
+        self.tokenizer = tokenizer
+        self.start_len = input_ids.shape[1]
+
+    def call_for_batch(self, output_ids, scores=None, **kw):
+        offset = min(output_ids.shape[1] - self.start_len, self.max_keyword_len)
+        for kid in self.keyword_ids:
+            kid = kid.to(output_ids.device)
+            if kid.numel() and output_ids.shape[1] >= kid.shape[0] and bool((output_ids[0, -kid.shape[0]:] == kid).all()):
+                return True
+        if offset <= 0:
+            return False
+        text = self.tokenizer.batch_decode(output_ids[:, -offset:], skip_special_tokens=True)[0]
+        return any(kw_ in text for kw_ in self.keywords)
+
+    def __call__(self, output_ids, scores=None, **kw):
+        return all(self.call_for_batch(output_ids[i].unsqueeze(0), scores) for i in range(output_ids.shape[0]))

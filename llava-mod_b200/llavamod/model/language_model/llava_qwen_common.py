@@ -107,6 +107,26 @@ class LlavaQwenForCausalLMBase(nn.Module, LlavaMetaForCausalLM):
             load_into(model, sd, strict=False)
         return model
 
+    # ---- eval path ---------------------------------------------------------------------
+    def generate(self, inputs=None, images=None, **kw):
+        """HF-style entry used by the reference's eval scripts (eval/model_vqa_loader.py:119-130); see model/generation.py."""
+        from ..generation import generate
+        if inputs is None:
+            inputs = kw.pop("input_ids")
+        return generate(self, inputs, images=images, **kw)
+
+    def resize_token_embeddings(self, new_num_tokens=None):
+        """builder.load_pretrained_model calls this with len(tokenizer) (builder.py:588).  HF would cut (or grow) the embedding / lm_head
+        matrices; here the storage keeps its checkpoint size and decoding masks the logits beyond the active vocabulary -- the same
+        distribution over the same tokens.  Growing past the checkpoint's vocabulary would need new rows and is refused."""
+        if new_num_tokens is None:
+            return self.model.embed_tokens
+        if new_num_tokens > self.model.embed_tokens.weight.shape[0]:
+            raise NotImplementedError("resize_token_embeddings beyond the checkpoint vocabulary (%d > %d)" %
+                                      (new_num_tokens, self.model.embed_tokens.weight.shape[0]))
+        self._active_vocab = int(new_num_tokens)
+        return self.model.embed_tokens
+
     # ---- forward -------------------------------------------------------------------------------------
     def forward_hidden(self, input_ids=None, attention_mask=None, position_ids=None, inputs_embeds=None, labels=None,
                        images=None, moe_noise=None, tower_features=None, plan=None):
