@@ -236,13 +236,24 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# our arm
+# our arm  (nothing in it imports oracle/ or tests/: the oracle is used by the cpu_baseline / --impl reference legs only)
 # ---------------------------------------------------------------------------------------------------------------------
+def make_trainer(student, teacher, loss_type="kd_lm", accum=1, lr=2e-5, max_steps=100):
+    from llavamod.config.args import TrainingArguments
+    from llavamod.train.align_trainer import AlignTrainer
+    targs = TrainingArguments(output_dir="/tmp/lmod_out", per_device_train_batch_size=1, gradient_accumulation_steps=accum, learning_rate=lr,
+                              weight_decay=0.0, warmup_ratio=0.03, lr_scheduler_type="cosine", max_steps=max_steps, logging_steps=0,
+                              save_strategy="no", bf16=True)
+    targs.moe_enable = True
+    tr = AlignTrainer(model=student, ref_model=teacher, args=targs, loss_type=loss_type, moe_loss_enable=True)
+    tr._total_steps = max_steps
+    return tr
+
+
 def run_ours(args):
     import torch.distributed as dist
     from llavamod import _C, kernels as K
     from llavamod.model import synthetic as S
-    from tests.helpers import make_trainer
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
