@@ -16,10 +16,20 @@ Pinning status
   * DeepSpeed-0.9.5 MoE (``deepspeed.moe.sharded_moe.top2gating`` / ``MOELayer`` / ``Experts``):
     third-party, un-vendored, not installable here -> restated from the published algorithm
     (SURVEY.md Appendix A).  **parity unpinned** for this piece.
-  * trainers (``align_trainer.py:455-594``, ``dpo_trainer.py:462-641``): cannot be imported
-    (accelerate / deepspeed missing); restated line by line, checked by analytic known answers
-    (uniform logits -> log V; policy==ref -> log 2 / 0.5).  **parity unpinned** beyond that.
-  * optimizer / schedule (HF Trainer 4.37 + torch AdamW): **parity unpinned**.
+  * trainers (``align_trainer.py:455-594``, ``dpo_trainer.py:462-641``): the files cannot be imported
+    (accelerate / deepspeed missing), but their loss code is plain torch: the reference's own method
+    bodies (get_p / get_logp / compute_align_loss / compute_loss, DPO get_logp / dpo_loss /
+    compute_loss) are exec'd from the read-only tree on fake model outputs by
+    ``tests/golden/make_loss_golden.py`` and this module reproduces them in all 15 cases (-inf terms,
+    0/0 -> NaN, distill_all_tokens, both moe-loss branches incl. the -1.0 sentinel, every DPO loss
+    type, label smoothing): **pinned** (``tests/test_trainer_loss_pin.py``); plus analytic known
+    answers (uniform logits -> log V; policy==ref -> log 2 / 0.5).
+  * optimizer / schedule / clipping (HF Trainer 4.37 + torch AdamW): pinned against the installed
+    ``torch.optim.AdamW``, ``transformers.get_cosine_schedule_with_warmup`` and
+    ``torch.nn.utils.clip_grad_norm_`` over 40 steps (same test file) -- transformers here is 5.5,
+    not the reference's 4.37, whose formulas are the same.
+  * data pipeline: the reference's own ``data/`` code runs here -> ``tests/golden/data_pipeline.pt``
+    (``tests/test_data_pipeline.py``; the product's data modules are checked, the oracle has no copy).
 """
 from __future__ import annotations
 
