@@ -15,7 +15,9 @@ Pinning status
     ``tests/golden/make_golden.py``).
   * DeepSpeed-0.9.5 MoE (``deepspeed.moe.sharded_moe.top2gating`` / ``MOELayer`` / ``Experts``):
     third-party, un-vendored, not installable here -> restated from the published algorithm
-    (SURVEY.md Appendix A).  **parity unpinned** for this piece.
+    (SURVEY.md Appendix A).  **parity unpinned** for this piece; an independent token-by-token
+    simulation of the same published algorithm agrees with it on every routing decision
+    (``tests/test_gating_semantics.py``), and the CUDA router is bit-exact against it.
   * trainers (``align_trainer.py:455-594``, ``dpo_trainer.py:462-641``): the files cannot be imported
     (accelerate / deepspeed missing), but their loss code is plain torch: the reference's own method
     bodies (get_p / get_logp / compute_align_loss / compute_loss, DPO get_logp / dpo_loss /
