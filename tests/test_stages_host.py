@@ -85,3 +85,19 @@ def test_trainer_uses_the_length_grouped_sampler_per_rank():
         seen.append([i for batch in tr.get_train_dataloader() for i in batch])
     assert len(seen[0]) == len(seen[1]) == 8 and not set(seen[0]) & set(seen[1])
     assert sorted(seen[0] + seen[1]) == list(range(16))
+
+
+def test_load_tokenizer_from_a_local_directory(golden_dir, tmp_path):
+    """align_train.py:360-369,436-441: slow-or-fast AutoTokenizer from the checkpoint directory, right padding, `<|extra_0|>` as unk, pad = unk,
+    conversation template from --version."""
+    import os
+    from llavamod import conversation as C
+    from llavamod.train.align_train import load_tokenizer
+    from tests.golden.make_data_golden import load_tokenizer as golden_tokenizer
+    golden_tokenizer(os.path.join(golden_dir, "tiny_tokenizer.json")).save_pretrained(str(tmp_path))
+    tok = load_tokenizer(types.SimpleNamespace(version="qwen"), types.SimpleNamespace(cache_dir=None, model_max_length=64), str(tmp_path))
+    assert tok.unk_token == "<|extra_0|>" and tok.pad_token == tok.unk_token and tok.padding_side == "right" and tok.model_max_length == 64
+    assert C.default_conversation is C.conv_phi
+    with pytest.raises(NotImplementedError):
+        load_tokenizer(types.SimpleNamespace(version="llama_2"), types.SimpleNamespace(cache_dir=None, model_max_length=64), str(tmp_path))
+    C.set_default_conversation("qwen")
