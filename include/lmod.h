@@ -104,16 +104,20 @@ int lmod_align_loss_dense(const float* logp, const float* probs, int64_t ld, con
  *   outputs: logits [S,E] fp32, gates [S,E] fp32, idx [S,2] int32, row [S,2] int32 (-1 = dropped),
  *            w [S,2] fp32 (normalised, 0 if dropped), offsets [E+1] int32 (row ranges per expert),
  *            meta [4+E] fp32 {l_aux, capacity, rows_total, 0, exp_counts...}, xp [2S,H] bf16 permuted.
- *   sync_ws: >= 16 bytes of zero-initialised device scratch (grid barrier), reset by the kernel.
+ *   ws: lmod_moe_route_ws_elems(S, E) int32 elements of device scratch owned by this call (no initialisation needed; the
+ *       two kernels of the op -- gate, then seat+scatter -- exchange per-tile expert counts through it).  Ordinary launches of
+ *       ceil(S/16) small CTAs: no cooperative launch, no grid barrier, safe to run concurrently on several streams.
  */
 /* layout: 0 = compact expert rows ; 1 = capacity-padded slabs (offsets[e] = e*C) ; 2 = compact with every group padded to a
- * multiple of 128 rows (what lmod_grouped_gemm_bf16 wants; xp must be zero-initialised so padding rows are inert).
+ * multiple of 128 rows (what lmod_grouped_gemm_bf16 wants).  The padding rows of xp (alignment / unused capacity) are zeroed by the
+ * op itself, so xp needs no initialisation; rows past offsets[E] are not touched.
  * meta = {l_aux, capacity, rows_used, rows_end(=offsets[E]), exp_counts[E]}. */
 int lmod_moe_capacity(int64_t S, int E, float capacity_factor, int64_t min_capacity);
 int lmod_moe_route_scatter(const void* x, const float* wg, const float* noise, int64_t S, int64_t H,
                            int E, float capacity_factor, int64_t min_capacity, int layout,
                            float* logits, float* gates, int32_t* idx, int32_t* row, float* w,
-                           int32_t* offsets, float* meta, void* xp, int32_t* sync_ws, void* stream);
+                           int32_t* offsets, float* meta, void* xp, int32_t* ws, void* stream);
+int64_t lmod_moe_route_ws_elems(int64_t S, int E);
 /* combine einsum("sec,ecm->sm") with bf16-rounded weights + optional residual add (Appendix A step 11,
  * llava_qwen1_5_moe.py:167) */
 int lmod_moe_gather_combine(const void* y, const int32_t* row, const float* w, const void* residual,
@@ -213,14 +217,19 @@ int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ld
 /* ------------------------------------------------------------------------------------------
  * K7: flash-attention FORWARD on tcgen05/TMEM/TMA (modeling_qwen2.py:713-721 causal; CLIP non-causal), reading the fused RoPE'd
  * QKV buffer [batch*seq, (nh+2*nkv)*hd] in place (GQA by index).  hd in {64,128}.  out [batch*seq, nh*hd];
- * lse [batch, nh, seq] fp32 (natural-log LSE of the scaled scores -- what flash-attn's backward consumes) or NULL. */
+ * lse [batch, nh, seq] fp32 (natural-log LSE of the scaled scores, consumed by lmod_attn_bwd) or NULL.
+ * Padded batches (the additive 4-D mask of modeling_qwen2.py:1035-1040; the varlen un-pad of :600-641): kv_lo / kv_hi are int32
+ * [batch] device arrays giving the real key range [kv_lo[b], kv_hi[b]) of every batch row (right or left padding); a query row with
+ * no visible key attends to all keys (HF _unmask_unattended).  Both NULL = no padding. */
 int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
-                  float softmax_scale, void* out, int64_t ld_o, float* lse, void* stream);
+                  float softmax_scale, void* out, int64_t ld_o, float* lse, const int32_t* kv_lo, const int32_t* kv_hi,
+                  void* stream);
 /* flash-attention BACKWARD on tcgen05 (autograd of the call above): dqkv (fused dq|dk|dv, same layout as qkv) from qkv, out, dout, lse.
- * dq32_ws: fp32 [batch*seq, nh*hd] workspace (zeroed inside), dsum_ws: fp32 [batch, nh, seq] workspace. */
+ * dq32_ws: fp32 [batch*seq, nh*hd] workspace (zeroed inside), dsum_ws: fp32 [batch, nh, seq] workspace; kv_lo / kv_hi as above. */
 int lmod_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_o, const void* dout, int64_t ld_do,
                   const float* lse, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal, float softmax_scale,
-                  void* dqkv, int64_t ld_dqkv, float* dq32_ws, float* dsum_ws, void* stream);
+                  void* dqkv, int64_t ld_dqkv, float* dq32_ws, float* dsum_ws, const int32_t* kv_lo, const int32_t* kv_hi,
+                  void* stream);
 
 
 #ifdef __cplusplus

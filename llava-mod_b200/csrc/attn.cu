@@ -5,6 +5,8 @@
 // QKV projection output [B*T, (nh + 2*nkv)*hd] -- no head transposes, GQA by index (repeat_kv :204-213 never materialises).
 //
 // One CTA = one (batch, head, 128-query block); two CTAs are co-resident per SM so one CTA's softmax overlaps the other's MMAs.
+// Padded batches (right or left padding, per-row key range [kv_lo, kv_hi)) run on the same kernel: the CTA walks only the key blocks
+// its rows can see and masks per element; rows with no visible key are un-masked as in the reference's 4-D mask.
 //   warp 0 lane 0 : TMA producer -- Q tile once, K/V blocks of 64 keys through a 2-stage 128B-swizzled ring
 //   warp 1 lane 0 : MMA issuer   -- S_j = Q K_j^T (SS, M=128 N=64 K=16 x hd/16) into one of two S buffers in TMEM;
 //                                   O += P_j V_j (TS: A = P_j read from TMEM, B = V_j MN-major from smem, N = hd)
@@ -28,7 +30,27 @@ struct AttnParams {
   int B, T, nh, nkv;
   int causal;
   float scale_log2;      // softmax_scale * log2(e)
+  // padded batches (the reference's additive 4-D mask, modeling_qwen2.py:1035-1040): per batch row the keys [kv_lo, kv_hi) are real
+  // tokens, everything else is padding.  Query rows that see no key at all (left padding) are un-masked like HF's
+  // _unmask_unattended: they attend to every key of the row, causal mask dropped.  NULL = no padding.
+  const int32_t* kv_lo;
+  const int32_t* kv_hi;
 };
+
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): two lanes of a row per issue slot -- the softmax warps are issue-bound
+__device__ __forceinline__ void ffma2_bc(float& d0, float& d1, float a0, float a1, float b, float c) {     // d = a * b + c, b and c broadcast
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mov.b64 rc, {%5,%5}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
+  asm("{ .reg .b64 ra, rd; mov.b64 ra, {%2,%3}; mov.b64 rd, {%0,%1}; add.rn.f32x2 rd, rd, ra; mov.b64 {%0,%1}, rd; }"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void fmul2_bc(float& d0, float& d1, float b) {
+  asm("{ .reg .b64 rb, rd; mov.b64 rd, {%0,%1}; mov.b64 rb, {%2,%2}; mul.rn.f32x2 rd, rd, rb; mov.b64 {%0,%1}, rd; }"
+      : "+f"(d0), "+f"(d1) : "f"(b));
+}
+constexpr float RESCALE_TAU = 8.0f;     // lazy rescale: the running max is only raised when a block max exceeds it by > 2^8 (log2 units)
 
 // instruction descriptor: F32 accumulate, BF16 inputs, M = 128, N = n ; b_mn selects the B major-ness
 __device__ __forceinline__ uint32_t attn_idesc(int n, bool b_mn) {
@@ -64,8 +86,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.nh / p.nkv);
   const int q0 = qb * BQ;
-  const int kv_len = p.causal ? min(p.T, q0 + BQ) : p.T;
-  const int nblk = (kv_len + BKV - 1) / BKV;
+  int lo = 0, hi = p.T;
+  if (p.kv_lo) { lo = p.kv_lo[b]; hi = p.kv_hi[b]; }
+  const bool all_pad = hi <= lo;
+  // key blocks this CTA walks: [jb, jb + nblk).  A block that holds an un-masked row (no visible key) walks every key.
+  int kbeg = lo, kend = p.causal ? min(hi, q0 + BQ) : hi;
+  if (all_pad || q0 < lo) { kbeg = 0; kend = p.T; }
+  const int jb = kbeg / BKV;
+  const int nblk = (kend + BKV - 1) / BKV - jb;
   const int row_base = b * p.T;                       // row of token 0 of this batch in the fused buffer
   const int col_q = h * HD, col_k = (p.nh + hk) * HD, col_v = (p.nh + p.nkv + hk) * HD;
 
@@ -97,8 +125,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
 #pragma unroll
       for (int i = 0; i < KSUB; ++i) {
-        tma_load_2d(sK + i * (BKV * 128), &tma_kv, col_k + 64 * i, row_base + j * BKV, &kv_full[s]);
-        tma_load_2d(sV + i * (BKV * 128), &tma_kv, col_v + 64 * i, row_base + j * BKV, &kv_full[s]);
+        tma_load_2d(sK + i * (BKV * 128), &tma_kv, col_k + 64 * i, row_base + (jb + j) * BKV, &kv_full[s]);
+        tma_load_2d(sV + i * (BKV * 128), &tma_kv, col_v + 64 * i, row_base + (jb + j) * BKV, &kv_full[s]);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -146,56 +174,68 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     const int qrow = q0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     constexpr int HC = HD / 2;                        // O columns per group
-    float m = -INFINITY, l = 0.f;
+    // keys this row may see: [klo_r, khi_r)
+    int klo_r = lo, khi_r = p.causal ? min(hi, qrow + 1) : hi;
+    if (all_pad || qrow < lo) { klo_r = 0; khi_r = p.T; }
+    float m = -INFINITY, l0 = 0.f, l1 = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
       mbar_wait_warp(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
       uint32_t sv[32];
       tmem_ld32(tS0 + s * BKV + g * 32 + lane_off, sv);
-      const int kv0 = j * BKV + g * 32;
-      const bool need_mask = (p.causal && kv0 + 31 > q0) || (kv0 + 32 > p.T);
-      float mx_loc = -INFINITY;
+      const int kv0 = (jb + j) * BKV + g * 32;
+      const bool need_mask = (kv0 < klo_r) || (kv0 + 32 > khi_r);
       if (need_mask) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int kv = kv0 + c;
-          float x = __uint_as_float(sv[c]);
-          if (kv >= p.T || (p.causal && kv > qrow)) x = -INFINITY;
-          sv[c] = __float_as_uint(x);
-          mx_loc = fmaxf(mx_loc, x);
+          if (kv < klo_r || kv >= khi_r) sv[c] = 0xff800000u;      // -inf
         }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) mx_loc = fmaxf(mx_loc, __uint_as_float(sv[c]));
       }
+      float mx_loc = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) mx_loc = fmaxf(mx_loc, fmaxf(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])));
       xmax[s][g][r] = mx_loc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mx = fmaxf(m, fmaxf(mx_loc, xmax[s][g ^ 1][r]) * p.scale_log2);   // running max in scaled-log2 units (scale > 0)
-      const float m_use = (mx == -INFINITY) ? 0.f : mx;     // fully masked so far (rows >= T only): keep everything finite
-      const float alpha = ex2f(m - m_use);                   // m = -inf on the first block -> 0
+      const float mblk = fmaxf(mx_loc, xmax[s][g ^ 1][r]) * p.scale_log2;     // block max in scaled-log2 units (scale > 0); both threads of a row agree
+      // lazy running max: keep the stale max while the block max stays within 2^TAU of it (P <= 2^TAU, exact in fp32 / fine in bf16); the
+      // O rescale -- a TMEM round trip that also has to wait for the previous P*V -- then happens on a few early blocks only
+      const bool upd = mblk > m + RESCALE_TAU;               // m = -inf on the first block with a visible key
+      const float m_new = upd ? mblk : m;
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // no visible key so far: keep everything finite (P = exp2(-inf) = 0)
+      const float alpha = upd ? ex2f(m - m_new) : 1.f;       // m = -inf -> 0
+      m = m_new;
+      const float neg_m = -m_use;
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pk[16];
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
-        const float p0 = ex2f(fmaf(__uint_as_float(sv[c]), p.scale_log2, -m_use));
-        const float p1 = ex2f(fmaf(__uint_as_float(sv[c + 1]), p.scale_log2, -m_use));
-        rs0 += p0; rs1 += p1;
+        float t0, t1;
+        ffma2_bc(t0, t1, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]), p.scale_log2, neg_m);
+        const float p0 = ex2f(t0), p1 = ex2f(t1);
+        fadd2_acc(rs0, rs1, p0, p1);
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
-      l = l * alpha + (rs0 + rs1);
-      const bool moved = mx > m;
-      m = mx;
+      l0 = fmaf(l0, alpha, rs0);
+      l1 = fmaf(l1, alpha, rs1);
       if (j > 0) {
-        mbar_wait_warp(&pv_done, (j - 1) & 1);               // O holds blocks 0..j-1
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, moved)) {                // rescale this group's half of O only when a row of the warp raised its max
+        const bool any_upd = __any_sync(0xffffffffu, upd);
+        if (any_upd || j == nblk - 1) {                      // (the last block always waits: it keeps the epilogue's parity wait unambiguous)
+          mbar_wait_warp(&pv_done, (j - 1) & 1);             // O holds blocks 0..j-1
+          tc_fence_after();
+        }
+        if (any_upd) {                                       // rescale this group's half of O
 #pragma unroll
           for (int c = 0; c < HC / 32; ++c) {
             uint32_t o[32];
             tmem_ld32(tO + g * HC + c * 32 + lane_off, o);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            for (int i = 0; i < 32; i += 2) {
+              float a0 = __uint_as_float(o[i]), a1 = __uint_as_float(o[i + 1]);
+              fmul2_bc(a0, a1, alpha);
+              o[i] = __float_as_uint(a0); o[i + 1] = __float_as_uint(a1);
+            }
             tmem_st32(tO + g * HC + c * 32 + lane_off, o);
           }
         }
@@ -206,6 +246,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[s]);
     }
+    const float l = l0 + l1;
     // ---- epilogue: combine the two partial row sums, normalise, store this group's half of the head dimension ----
     xsum[g][r] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -256,8 +297,11 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams&
 
 // qkv: fused projection output [batch*seq, (nh + 2*nkv)*hd] bf16 (q heads | k heads | v heads), row stride ld_qkv.
 // out: [batch*seq, nh*hd] (row stride ld_o).  lse: [batch, nh, seq] fp32 or NULL.  hd in {64, 128}.
+// kv_lo / kv_hi: int32 [batch] device arrays, the real (un-padded) key range of every batch row, or both NULL for no padding.
 extern "C" int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
-                             float softmax_scale, void* out, int64_t ld_o, float* lse, void* stream) {
+                             float softmax_scale, void* out, int64_t ld_o, float* lse, const int32_t* kv_lo, const int32_t* kv_hi,
+                             void* stream) {
+  LMOD_CHECK_ARG((kv_lo == nullptr) == (kv_hi == nullptr), "lmod_attn_fwd: kv_lo and kv_hi come together");
   LMOD_CHECK_ARG(qkv && out && batch > 0 && seq > 0 && nh > 0 && nkv > 0 && nh % nkv == 0, "lmod_attn_fwd: bad arguments");
   LMOD_CHECK_ARG(hd == 64 || hd == 128, "lmod_attn_fwd: head_dim %d not built (64 and 128 are)", hd);
   LMOD_CHECK_ARG(ld_qkv % 8 == 0 && ld_o % 8 == 0 && ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 16 == 0), "lmod_attn_fwd: alignment");
@@ -270,5 +314,6 @@ extern "C" int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int
   AttnParams p;
   p.out = (__nv_bfloat16*)out; p.lse = lse; p.ld_o = ld_o; p.B = (int)batch; p.T = (int)seq; p.nh = nh; p.nkv = nkv; p.causal = causal;
   p.scale_log2 = softmax_scale * LOG2E_F;
+  p.kv_lo = kv_lo; p.kv_hi = kv_hi;
   return hd == 128 ? launch_attn<128>(tq, tkv, p, (cudaStream_t)stream) : launch_attn<64>(tq, tkv, p, (cudaStream_t)stream);
 }

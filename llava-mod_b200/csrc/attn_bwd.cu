@@ -29,6 +29,8 @@ struct AttnBwdParams {
   int B, T, nh, nkv;
   int causal;
   float scale, scale_log2;
+  const int32_t* kv_lo;   // padded batches: real key range per batch row (see attn.cu); NULL = no padding
+  const int32_t* kv_hi;
 };
 
 __device__ __forceinline__ uint32_t bwd_idesc(int m, int n, bool a_mn, bool b_mn) {
@@ -77,7 +79,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_kv, const __grid_constan
   const int group = p.nh / p.nkv;
   const int kv0 = j * BKVB;
   const int nq = (p.T + BQB - 1) / BQB;
-  const int i_start = p.causal ? (kv0 / BQB) : 0;
+  int lo = 0, hi = p.T;
+  if (p.kv_lo) { lo = p.kv_lo[b]; hi = p.kv_hi[b]; }
+  const bool all_pad = hi <= lo;
+  const bool padded = (lo > 0) || (hi < p.T);
+  // un-masked query rows (rows in front of a left-padded sequence see every key) make every query block a partner of this key block
+  const int i_start = (p.causal && lo == 0 && !all_pad) ? (kv0 / BQB) : 0;
   const int n_i = nq - i_start;                        // query blocks per head for this key block
   const int n_it = n_i * group;
   const int row_base = b * p.T;
@@ -211,7 +218,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_kv, const __grid_constan
       const float* lse2 = s_lse2[it & 1] + g * 32;
       const float* dsm_s = s_dsum[it & 1] + g * 32;
       // only the blocks on the causal diagonal and the ragged tail need per-element masks
-      const bool masked = (q0 + BQB > p.T) || (kv0 + BKVB > p.T) || (p.causal && q0 < kv0 + BKVB - 1);
+      const bool masked = padded || (q0 + BQB > p.T) || (kv0 + BKVB > p.T) || (p.causal && q0 < kv0 + BKVB - 1);
       mbar_wait_warp(&s_full[buf], (it / NBUF) & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -225,7 +232,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_kv, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int qidx = q0 + g * 32 + c + e;
-            const bool ok = (qidx < p.T) && (kv < p.T) && (!p.causal || kv <= qidx);
+            const bool seen = (all_pad || qidx < lo) ? true : (kv >= lo && kv < hi && (!p.causal || kv <= qidx));
+            const bool ok = (qidx < p.T) && (kv < p.T) && seen;
             const float pv = ok ? ex2f(fmaf(__uint_as_float(sv[c + e]), p.scale_log2, -lse2[c + e])) : 0.f;
             pp[e] = pv;
             dd[e] = pv * (__uint_as_float(dv[c + e]) - dsm_s[c + e]) * p.scale;
@@ -397,9 +405,11 @@ int launch_attn_bwd(const CUtensorMap& tkv, const CUtensorMap& tq, const CUtenso
 
 // qkv / dqkv: fused [batch*seq, (nh+2nkv)*hd]; out, dout: [batch*seq, nh*hd]; lse [batch, nh, seq] from lmod_attn_fwd.
 // dq32_ws: fp32 [batch*seq, nh*hd] workspace, dsum_ws: fp32 [batch, nh, seq] workspace (both written here; dq32 is zeroed inside).
+// kv_lo / kv_hi: as in lmod_attn_fwd (padded batches), or NULL.
 extern "C" int lmod_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_o, const void* dout, int64_t ld_do, const float* lse,
                              int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal, float softmax_scale, void* dqkv, int64_t ld_dqkv,
-                             float* dq32_ws, float* dsum_ws, void* stream) {
+                             float* dq32_ws, float* dsum_ws, const int32_t* kv_lo, const int32_t* kv_hi, void* stream) {
+  LMOD_CHECK_ARG((kv_lo == nullptr) == (kv_hi == nullptr), "lmod_attn_bwd: kv_lo and kv_hi come together");
   LMOD_CHECK_ARG(qkv && out && dout && lse && dqkv && dq32_ws && dsum_ws && batch > 0 && seq > 0 && nh % nkv == 0, "lmod_attn_bwd: bad arguments");
   LMOD_CHECK_ARG(hd == 64 || hd == 128, "lmod_attn_bwd: head_dim %d not built (64 and 128 are)", hd);
   LMOD_CHECK_ARG(ld_qkv % 8 == 0 && ld_o % 8 == 0 && ld_do % 8 == 0 && ld_dqkv % 8 == 0, "lmod_attn_bwd: strides must be multiples of 8");
@@ -425,6 +435,7 @@ extern "C" int lmod_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, i
   AttnBwdParams p;
   p.lse = lse; p.dsum = dsum_ws; p.dq32 = dq32_ws; p.dqkv = (__nv_bfloat16*)dqkv; p.ld_dqkv = ld_dqkv; p.ld_dq32 = qcols;
   p.B = (int)batch; p.T = (int)seq; p.nh = nh; p.nkv = nkv; p.causal = causal; p.scale = softmax_scale; p.scale_log2 = softmax_scale * LOG2E_F;
+  p.kv_lo = kv_lo; p.kv_hi = kv_hi;
   rc = (hd == 128) ? launch_attn_bwd<128>(tkv, tq, tdo, p, st) : launch_attn_bwd<64>(tkv, tq, tdo, p, st);
   if (rc) return rc;
   const int64_t n = rows * (qcols / 8);

@@ -1,16 +1,15 @@
-// moe.cu -- DeepSpeed-0.9.5 top-2 MoE routing on B200: gate + capacity + token scatter fused in one
-// cooperative kernel; weighted gather/combine; and their backward kernels.
+// moe.cu -- DeepSpeed-0.9.5 top-2 MoE routing on B200: gate (GEMV + softmax + top-2) and seat+scatter (stable capacity positions by
+// warp ballots, token copy) as two ordinary launches of small CTAs; weighted gather/combine; and their backward kernels.
 //
 // Replaces (third-party, call site llavamod/model/language_model/llava_qwen1_5_moe.py:536-546)
 // deepspeed.moe.sharded_moe.TopKGate / top2gating / MOELayer dispatch+combine einsums
 // (SURVEY.md Appendix A): ~40 small ATen kernels, a D2H sync (exp_counts.to('cpu')) and two one-hot
-// einsums per MoE layer become: route_scatter (1 launch) + expert GEMMs + gather_combine (1 launch).
+// einsums per MoE layer become: route_scatter (2 launches) + expert GEMMs + gather_combine (1 launch).
 //
 // Semantics kept bit-exact for the integer record (idx1, idx2, slot, kept) given the same fp32 logits
 // and the same Gumbel noise tensor: first choices are seated before any second choice, positions are
 // a STABLE prefix count over the flattened [B*T] token order (warp-ballot + popc, no atomics races),
 // capacity C = ceil(S/E * cf * 2), drops by position >= C.
-#include <cooperative_groups.h>
 #include <float.h>
 #include "common.cuh"
 
@@ -19,6 +18,9 @@ namespace {
 constexpr int RT_THREADS = 256;
 constexpr int RT_WARPS = RT_THREADS / 32;
 constexpr int MAXE = 8;
+constexpr int TOK_PER_WARP = 2;                       // a warp gates two tokens at a time (both rows in flight, one pass over wg)
+constexpr int TILE_MIN = RT_WARPS * TOK_PER_WARP;     // 16 tokens per CTA
+constexpr int MAX_TILES = 1024;
 
 struct RouteParams {
   const __nv_bfloat16* x;
@@ -27,200 +29,221 @@ struct RouteParams {
   int S, H, E;
   int capacity;
   int layout;            // 0: compact rows ; 1: offsets[e] = e*capacity (capacity-padded slabs) ; 2: compact, groups aligned to 128 rows
-  int stage_cap;         // tokens per block whose rows are kept in shared memory across the grid barrier
+  int tpb, ntiles;       // tokens per CTA (multiple of 16), number of CTAs
   float* logits; float* gates; int32_t* idx; int32_t* row; float* w;
   int32_t* offsets; float* meta; __nv_bfloat16* xp;
-  unsigned int* sync_ws;
+  int32_t* tile_cnt;     // [ntiles][2*MAXE]: first-choice counts per expert, then second-choice counts
+  float* tile_gsum;      // [ntiles][MAXE]: sum of gates per expert over the tile's tokens (token order)
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned int* ws, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(&ws[0], 1u);
-    while (*reinterpret_cast<volatile unsigned int*>(&ws[0]) < nblocks) { __nanosleep(64); }
-    __threadfence();
-    unsigned int left = atomicAdd(&ws[1], 1u);
-    if (left == nblocks - 1) { ws[0] = 0u; ws[1] = 0u; __threadfence(); }   // last one out re-arms the barrier
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(RT_THREADS, 1) moe_route_scatter_kernel(const RouteParams p) {
+// ---- kernel 1 of 2: gate.  fp32 GEMV against wg (staged in shared memory), softmax, top-1, Gumbel top-2; per-tile expert counts ----
+// An ordinary launch of ceil(S/16) small CTAs (no cooperative launch, no grid barrier): it shares the machine with whatever else is
+// running (the frozen teacher's GEMMs on the side stream).
+__global__ void __launch_bounds__(RT_THREADS) moe_gate_kernel(const RouteParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  // layout: wg fp32 [E,H] | stage bf16 [stage_cap,H] | idx bytes [2*S] | small arrays
-  float* s_wg = reinterpret_cast<float*>(smem);
-  __nv_bfloat16* s_stage = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)p.E * p.H * 4);
-  uint8_t* s_idx = smem + (size_t)p.E * p.H * 4 + (size_t)p.stage_cap * p.H * 2;
-  __shared__ int s_tot1[MAXE], s_tot2[MAXE], s_pre1[MAXE], s_pre2[MAXE], s_off[MAXE + 1];
-  __shared__ float s_red[32];
-
+  float* s_wg = reinterpret_cast<float*>(smem);                           // [E,H] fp32
+  float* s_gates = s_wg + (size_t)p.E * p.H;                              // [tpb][MAXE]
+  __shared__ int s_cnt[2 * MAXE];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int G = gridDim.x;
-  const int tpb = (p.S + G - 1) / G;
-  const int b0 = min(p.S, (int)blockIdx.x * tpb), b1 = min(p.S, b0 + tpb);
   const int E = p.E, H = p.H, hv = H >> 3;
+  const int b0 = min(p.S, (int)blockIdx.x * p.tpb), b1 = min(p.S, b0 + p.tpb);
 
   for (int i = tid; i < E * H / 4; i += RT_THREADS)
-    reinterpret_cast<float4*>(s_wg)[i] = reinterpret_cast<const float4*>(p.wg)[i];
-  if (tid < MAXE) { s_tot1[tid] = 0; s_tot2[tid] = 0; s_pre1[tid] = 0; s_pre2[tid] = 0; }
+    reinterpret_cast<float4*>(s_wg)[i] = __ldg(reinterpret_cast<const float4*>(p.wg) + i);
+  if (tid < 2 * MAXE) s_cnt[tid] = 0;
   __syncthreads();
 
-  // ---------------- phase 1: gate (warp per token), stage the token rows in shared memory ----------------
-  for (int tok = b0 + warp; tok < b1; tok += RT_WARPS) {
-    const int loc = tok - b0;
-    const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)tok * H);
-    float acc[MAXE];
+  for (int t0 = b0 + warp * TOK_PER_WARP; t0 < b1; t0 += RT_WARPS * TOK_PER_WARP) {
+    const bool has1 = t0 + 1 < b1;
+    const uint4* xr0 = reinterpret_cast<const uint4*>(p.x + (size_t)t0 * H);
+    const uint4* xr1 = reinterpret_cast<const uint4*>(p.x + (size_t)(has1 ? t0 + 1 : t0) * H);
+    float acc0[MAXE], acc1[MAXE];
 #pragma unroll
-    for (int e = 0; e < MAXE; ++e) acc[e] = 0.f;
+    for (int e = 0; e < MAXE; ++e) { acc0[e] = 0.f; acc1[e] = 0.f; }
     for (int v = lane; v < hv; v += 32) {
-      uint4 u = ldg_nc_v4(xr + v);
-      if (loc < p.stage_cap) reinterpret_cast<uint4*>(s_stage + (size_t)loc * H)[v] = u;
-      float xf[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+      const uint4 u0 = ldg_nc_v4(xr0 + v), u1 = ldg_nc_v4(xr1 + v);
+      const float xf[8] = {bf16lo(u0.x), bf16hi(u0.x), bf16lo(u0.y), bf16hi(u0.y), bf16lo(u0.z), bf16hi(u0.z), bf16lo(u0.w), bf16hi(u0.w)};
+      const float yf[8] = {bf16lo(u1.x), bf16hi(u1.x), bf16lo(u1.y), bf16hi(u1.y), bf16lo(u1.z), bf16hi(u1.z), bf16lo(u1.w), bf16hi(u1.w)};
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
         if (e < E) {
           const float4 w0 = *reinterpret_cast<const float4*>(s_wg + (size_t)e * H + v * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(s_wg + (size_t)e * H + v * 8 + 4);
-          acc[e] = fmaf(xf[0], w0.x, acc[e]); acc[e] = fmaf(xf[1], w0.y, acc[e]);
-          acc[e] = fmaf(xf[2], w0.z, acc[e]); acc[e] = fmaf(xf[3], w0.w, acc[e]);
-          acc[e] = fmaf(xf[4], w1.x, acc[e]); acc[e] = fmaf(xf[5], w1.y, acc[e]);
-          acc[e] = fmaf(xf[6], w1.z, acc[e]); acc[e] = fmaf(xf[7], w1.w, acc[e]);
+          acc0[e] = fmaf(xf[0], w0.x, acc0[e]); acc0[e] = fmaf(xf[1], w0.y, acc0[e]);
+          acc0[e] = fmaf(xf[2], w0.z, acc0[e]); acc0[e] = fmaf(xf[3], w0.w, acc0[e]);
+          acc0[e] = fmaf(xf[4], w1.x, acc0[e]); acc0[e] = fmaf(xf[5], w1.y, acc0[e]);
+          acc0[e] = fmaf(xf[6], w1.z, acc0[e]); acc0[e] = fmaf(xf[7], w1.w, acc0[e]);
+          acc1[e] = fmaf(yf[0], w0.x, acc1[e]); acc1[e] = fmaf(yf[1], w0.y, acc1[e]);
+          acc1[e] = fmaf(yf[2], w0.z, acc1[e]); acc1[e] = fmaf(yf[3], w0.w, acc1[e]);
+          acc1[e] = fmaf(yf[4], w1.x, acc1[e]); acc1[e] = fmaf(yf[5], w1.y, acc1[e]);
+          acc1[e] = fmaf(yf[6], w1.z, acc1[e]); acc1[e] = fmaf(yf[7], w1.w, acc1[e]);
         }
       }
     }
 #pragma unroll
-    for (int e = 0; e < MAXE; ++e) acc[e] = warp_sum(acc[e]);
-    if (lane == 0) {
+    for (int e = 0; e < MAXE; ++e) { acc0[e] = warp_sum(acc0[e]); acc1[e] = warp_sum(acc1[e]); }
+    if (lane == 1) {
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) acc0[e] = acc1[e];
+    }
+    if (lane == 0 || (lane == 1 && has1)) {          // lane 0 finishes token t0, lane 1 token t0+1
+      const int tok = t0 + lane;
       float mx = -INFINITY;
       int i1 = 0;
 #pragma unroll
-      for (int e = 0; e < MAXE; ++e) if (e < E && acc[e] > mx) { mx = acc[e]; i1 = e; }   // first max wins ties
+      for (int e = 0; e < MAXE; ++e) if (e < E && acc0[e] > mx) { mx = acc0[e]; i1 = e; }   // first max wins ties
       float ex[MAXE], den = 0.f;
 #pragma unroll
-      for (int e = 0; e < MAXE; ++e) { ex[e] = (e < E) ? expf(acc[e] - mx) : 0.f; den += ex[e]; }
+      for (int e = 0; e < MAXE; ++e) { ex[e] = (e < E) ? expf(acc0[e] - mx) : 0.f; den += ex[e]; }
       float best = -INFINITY;
       int i2 = (i1 == 0) ? 1 : 0;
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
         if (e < E && e != i1) {
-          float v = acc[e] + p.noise[(size_t)tok * E + e];
+          const float v = acc0[e] + p.noise[(size_t)tok * E + e];
           if (v > best) { best = v; i2 = e; }
         }
       }
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
-        if (e < E) { p.logits[(size_t)tok * E + e] = acc[e]; p.gates[(size_t)tok * E + e] = ex[e] / den; }
+        const float g = ex[e] / den;
+        if (e < E) { p.logits[(size_t)tok * E + e] = acc0[e]; p.gates[(size_t)tok * E + e] = g; }
+        s_gates[(tok - b0) * MAXE + e] = (e < E) ? g : 0.f;
       }
       p.idx[2 * tok] = i1; p.idx[2 * tok + 1] = i2;
+      atomicAdd(&s_cnt[i1], 1);
+      atomicAdd(&s_cnt[MAXE + i2], 1);
     }
-  }
-
-  grid_barrier(p.sync_ws, G);
-
-  // ---------------- phase 2: stable positions (every block recomputes the global prefix counts) ----------------
-  for (int i = tid; i < p.S; i += RT_THREADS) {
-    int2 v = __ldcg(reinterpret_cast<const int2*>(p.idx) + i);
-    s_idx[2 * i] = (uint8_t)v.x; s_idx[2 * i + 1] = (uint8_t)v.y;
   }
   __syncthreads();
+  if (tid < 2 * MAXE) p.tile_cnt[(size_t)blockIdx.x * 2 * MAXE + tid] = s_cnt[tid];
+  if (tid >= 32 && tid < 32 + MAXE) {                 // per-expert gate mass of the tile, summed in token order (deterministic l_aux)
+    const int e = tid - 32;
+    float a = 0.f;
+    for (int t = 0; t < b1 - b0; ++t) a += s_gates[t * MAXE + e];
+    p.tile_gsum[(size_t)blockIdx.x * MAXE + e] = a;
+  }
+}
+
+// ---- kernel 2 of 2: seat + scatter.  Every CTA rebuilds the global per-expert totals and its own exclusive prefix from the tile
+// counts (a few KB, L2 resident), seats its tokens in token order with warp ballots + popc (all first choices before any second
+// choice, drop at position >= capacity), renormalises the two gate weights, and copies its token rows to their expert rows. ----
+__global__ void __launch_bounds__(RT_THREADS) moe_seat_scatter_kernel(const RouteParams p) {
+  __shared__ int s_tot[2 * MAXE], s_pre[2 * MAXE], s_off[MAXE + 1], s_used[MAXE];
+  __shared__ int s_row[2 * 32 * 64];                  // rows of this CTA's tokens (tpb <= 1024... see launch: tpb*2 <= 4096)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E = p.E, H = p.H, hv = H >> 3;
+  const int tile = blockIdx.x;
+  const int b0 = min(p.S, tile * p.tpb), b1 = min(p.S, b0 + p.tpb);
+  if (tid < 2 * MAXE) { s_tot[tid] = 0; s_pre[tid] = 0; }
+  __syncthreads();
   {
-    int t1[MAXE], t2[MAXE], q1[MAXE], q2[MAXE];
-#pragma unroll
-    for (int e = 0; e < MAXE; ++e) { t1[e] = t2[e] = q1[e] = q2[e] = 0; }
-    const int ngroups = (p.S + 31) >> 5;
-    for (int g = warp; g < ngroups; g += RT_WARPS) {
-      const int tok = (g << 5) + lane;
-      const bool valid = tok < p.S;
-      const int e1 = valid ? s_idx[2 * tok] : -1, e2 = valid ? s_idx[2 * tok + 1] : -1;
-      const bool before = tok < b0;
-#pragma unroll
-      for (int e = 0; e < MAXE; ++e) {
-        if (e < E) {
-          unsigned a = __ballot_sync(0xffffffffu, e1 == e), b = __ballot_sync(0xffffffffu, e2 == e);
-          unsigned ab = __ballot_sync(0xffffffffu, before && e1 == e), bb = __ballot_sync(0xffffffffu, before && e2 == e);
-          t1[e] += __popc(a); t2[e] += __popc(b); q1[e] += __popc(ab); q2[e] += __popc(bb);
-        }
-      }
+    // lanes 0..15 / 16..31 read the 16 counters of two consecutive tiles per step
+    const int c = lane & 15;
+    int tot = 0, pre = 0;
+    for (int t = 2 * warp + (lane >> 4); t < p.ntiles; t += 2 * RT_WARPS) {
+      const int v = __ldg(p.tile_cnt + (size_t)t * 2 * MAXE + c);
+      tot += v;
+      if (t < tile) pre += v;
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int e = 0; e < MAXE; ++e) {
-        if (e < E) { atomicAdd(&s_tot1[e], t1[e]); atomicAdd(&s_tot2[e], t2[e]); atomicAdd(&s_pre1[e], q1[e]); atomicAdd(&s_pre2[e], q2[e]); }
-      }
-    }
+    tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+    pre += __shfl_xor_sync(0xffffffffu, pre, 16);
+    if (lane < 16) { atomicAdd(&s_tot[c], tot); atomicAdd(&s_pre[c], pre); }
   }
   __syncthreads();
   if (tid == 0) {
     int o = 0, used = 0;
     for (int e = 0; e < E; ++e) {
       s_off[e] = (p.layout == 1) ? e * p.capacity : o;
-      int rows_e = min(s_tot1[e] + s_tot2[e], p.capacity);
+      const int rows_e = min(s_tot[e] + s_tot[MAXE + e], p.capacity);
+      s_used[e] = rows_e;
       used += rows_e;
       o += (p.layout == 2) ? ((rows_e + 127) & ~127) : rows_e;
     }
     s_off[E] = (p.layout == 1) ? E * p.capacity : o;
-    if (blockIdx.x == 0) {
+    if (tile == 0) {
       for (int e = 0; e <= E; ++e) p.offsets[e] = s_off[e];
       p.meta[1] = (float)p.capacity; p.meta[2] = (float)used; p.meta[3] = (float)s_off[E];
-      for (int e = 0; e < E; ++e) p.meta[4 + e] = (float)s_tot1[e];
+      for (int e = 0; e < E; ++e) p.meta[4 + e] = (float)s_tot[e];
     }
   }
   __syncthreads();
-  // warp 0 seats this block's tokens in order (32 at a time, ballot + popc prefix)
+  // l_aux = E * sum_e mean_s(gates[:,e]) * mean_s(mask1[:,e])   (before capacity drops); tile sums added in a fixed order
+  if (tile == 0 && warp < E) {
+    float a = 0.f;
+    for (int t = lane; t < p.ntiles; t += 32) a += __ldg(p.tile_gsum + (size_t)t * MAXE + warp);
+    a = warp_sum(a);
+    if (lane == 0) s_row[warp] = __float_as_int((a / (float)p.S) * ((float)s_tot[warp] / (float)p.S));
+  }
+  __syncthreads();
+  if (tile == 0 && tid == 0) {
+    float laux = 0.f;
+    for (int e = 0; e < E; ++e) laux += __int_as_float(s_row[e]);
+    p.meta[0] = laux * (float)E;
+  }
+  __syncthreads();
+  // warp 0 seats this CTA's tokens in order (32 at a time, ballot + popc prefix)
   if (warp == 0) {
     int c1[MAXE], c2[MAXE];
 #pragma unroll
-    for (int e = 0; e < MAXE; ++e) { c1[e] = (e < E) ? s_pre1[e] : 0; c2[e] = (e < E) ? s_pre2[e] : 0; }
+    for (int e = 0; e < MAXE; ++e) { c1[e] = s_pre[e]; c2[e] = s_pre[MAXE + e]; }
     const unsigned lt = (1u << lane) - 1u;
     for (int base = b0; base < b1; base += 32) {
       const int tok = base + lane;
       const bool valid = tok < b1;
-      const int e1 = valid ? s_idx[2 * tok] : -1, e2 = valid ? s_idx[2 * tok + 1] : -1;
+      int e1 = -1, e2 = -1;
+      if (valid) { const int2 v = __ldg(reinterpret_cast<const int2*>(p.idx) + tok); e1 = v.x; e2 = v.y; }
       int loc1 = 0, loc2 = 0;
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
         if (e < E) {
-          unsigned a = __ballot_sync(0xffffffffu, e1 == e), b = __ballot_sync(0xffffffffu, e2 == e);
+          const unsigned a = __ballot_sync(0xffffffffu, e1 == e), b = __ballot_sync(0xffffffffu, e2 == e);
           if (e1 == e) loc1 = c1[e] + __popc(a & lt);
-          if (e2 == e) loc2 = s_tot1[e] + c2[e] + __popc(b & lt);
+          if (e2 == e) loc2 = s_tot[e] + c2[e] + __popc(b & lt);
           c1[e] += __popc(a); c2[e] += __popc(b);
         }
       }
       if (valid) {
         const bool k1 = loc1 < p.capacity, k2 = loc2 < p.capacity;
-        const float g1 = k1 ? __ldcg(p.gates + (size_t)tok * E + e1) : 0.f;
-        const float g2 = k2 ? __ldcg(p.gates + (size_t)tok * E + e2) : 0.f;
+        const float g1 = k1 ? __ldg(p.gates + (size_t)tok * E + e1) : 0.f;
+        const float g2 = k2 ? __ldg(p.gates + (size_t)tok * E + e2) : 0.f;
         const float den = fmaxf(g1 + g2, FLT_EPSILON);
-        p.row[2 * tok] = k1 ? s_off[e1] + loc1 : -1;
-        p.row[2 * tok + 1] = k2 ? s_off[e2] + loc2 : -1;
+        const int r1 = k1 ? s_off[e1] + loc1 : -1, r2 = k2 ? s_off[e2] + loc2 : -1;
+        p.row[2 * tok] = r1; p.row[2 * tok + 1] = r2;
         p.w[2 * tok] = g1 / den; p.w[2 * tok + 1] = g2 / den;
+        s_row[2 * (tok - b0)] = r1; s_row[2 * (tok - b0) + 1] = r2;
       }
     }
   }
-  // l_aux = E * sum_e mean_s(gates[:,e]) * mean_s(mask1[:,e])   (before capacity drops)
-  if (blockIdx.x == 0) {
-    float laux = 0.f;
-    for (int e = 0; e < E; ++e) {
-      float a = 0.f;
-      for (int s = tid; s < p.S; s += RT_THREADS) a += __ldcg(p.gates + (size_t)s * E + e);
-      a = block_sum(a, s_red);
-      laux += (a / (float)p.S) * ((float)s_tot1[e] / (float)p.S);
-    }
-    if (tid == 0) p.meta[0] = laux * (float)E;
-  }
-  __syncthreads();   // rows of this block's tokens (global, written by warp 0) visible to the block
-
-  // ---------------- phase 3: scatter the token rows to their expert rows ----------------
-  for (int tok = b0 + warp; tok < b1; tok += RT_WARPS) {
-    const int loc = tok - b0;
-    const int r1 = p.row[2 * tok], r2 = p.row[2 * tok + 1];
-    const uint4* src = (loc < p.stage_cap) ? reinterpret_cast<const uint4*>(s_stage + (size_t)loc * H)
-                                           : reinterpret_cast<const uint4*>(p.x + (size_t)tok * H);
+  __syncthreads();
+  // scatter the token rows to their expert rows (two tokens per warp in flight; the rows were just read by the gate kernel: L2 hits)
+  for (int t0 = b0 + warp * TOK_PER_WARP; t0 < b1; t0 += RT_WARPS * TOK_PER_WARP) {
+    const bool has1 = t0 + 1 < b1;
+    const int ra1 = s_row[2 * (t0 - b0)], ra2 = s_row[2 * (t0 - b0) + 1];
+    const int rb1 = has1 ? s_row[2 * (t0 + 1 - b0)] : -1, rb2 = has1 ? s_row[2 * (t0 + 1 - b0) + 1] : -1;
+    const uint4* xa = reinterpret_cast<const uint4*>(p.x + (size_t)t0 * H);
+    const uint4* xb = reinterpret_cast<const uint4*>(p.x + (size_t)(has1 ? t0 + 1 : t0) * H);
     for (int v = lane; v < hv; v += 32) {
-      uint4 u = src[v];
-      if (r1 >= 0) stg_v4(reinterpret_cast<uint4*>(p.xp + (size_t)r1 * H) + v, u);
-      if (r2 >= 0) stg_v4(reinterpret_cast<uint4*>(p.xp + (size_t)r2 * H) + v, u);
+      const uint4 ua = ldg_nc_v4(xa + v), ub = ldg_nc_v4(xb + v);
+      if (ra1 >= 0) stg_v4(reinterpret_cast<uint4*>(p.xp + (size_t)ra1 * H) + v, ua);
+      if (ra2 >= 0) stg_v4(reinterpret_cast<uint4*>(p.xp + (size_t)ra2 * H) + v, ua);
+      if (rb1 >= 0) stg_v4(reinterpret_cast<uint4*>(p.xp + (size_t)rb1 * H) + v, ub);
+      if (rb2 >= 0) stg_v4(reinterpret_cast<uint4*>(p.xp + (size_t)rb2 * H) + v, ub);
+    }
+  }
+  // zero the padding rows [offsets[e] + used[e], offsets[e+1]) (128-row alignment / capacity slabs): they are operands of the grouped
+  // wgrad reduction and must be inert.  Pad row q (global numbering over the experts) belongs to CTA q mod gridDim, one warp per row.
+  {
+    int q0 = 0;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = 0; e < E; ++e) {
+      const int first = s_off[e] + s_used[e], npad = s_off[e + 1] - first;
+      for (int q = (int)blockIdx.x * RT_WARPS + warp; q < q0 + npad; q += (int)gridDim.x * RT_WARPS) {
+        if (q < q0) continue;
+        uint4* dst = reinterpret_cast<uint4*>(p.xp + (size_t)(first + q - q0) * H);
+        for (int v = lane; v < hv; v += 32) stg_v4(dst + v, z);
+      }
+      q0 += npad;
     }
   }
 }
@@ -424,11 +447,25 @@ extern "C" int lmod_moe_capacity(int64_t S, int E, float capacity_factor, int64_
   return (int)ci;
 }
 
+static int route_tpb(int64_t S) {
+  int64_t tpb = TILE_MIN;
+  while ((S + tpb - 1) / tpb > MAX_TILES) tpb += TILE_MIN;
+  return (int)tpb;
+}
+
+// int32 elements of scratch lmod_moe_route_scatter needs (per call; no initialisation required): tile counts + tile gate sums
+extern "C" int64_t lmod_moe_route_ws_elems(int64_t S, int E) {
+  (void)E;
+  const int tpb = route_tpb(S);
+  const int64_t ntiles = (S + tpb - 1) / tpb;
+  return ntiles * (2 * MAXE + MAXE);
+}
+
 extern "C" int lmod_moe_route_scatter(const void* x, const float* wg, const float* noise, int64_t S, int64_t H, int E,
                                       float capacity_factor, int64_t min_capacity, int layout, float* logits, float* gates,
                                       int32_t* idx, int32_t* row, float* w, int32_t* offsets, float* meta, void* xp,
-                                      int32_t* sync_ws, void* stream) {
-  LMOD_CHECK_ARG(x && wg && noise && logits && gates && idx && row && w && offsets && meta && xp && sync_ws,
+                                      int32_t* ws, void* stream) {
+  LMOD_CHECK_ARG(x && wg && noise && logits && gates && idx && row && w && offsets && meta && xp && ws,
                  "lmod_moe_route_scatter: null pointer");
   LMOD_CHECK_ARG(E >= 2 && E <= MAXE, "lmod_moe_route_scatter: 2 <= E <= %d required (got %d)", MAXE, E);
   LMOD_CHECK_ARG(S > 0 && H > 0 && H % 8 == 0, "lmod_moe_route_scatter: H must be a multiple of 8");
@@ -438,28 +475,23 @@ extern "C" int lmod_moe_route_scatter(const void* x, const float* wg, const floa
   p.capacity = lmod_moe_capacity(S, E, capacity_factor, min_capacity);
   p.layout = layout;
   p.logits = logits; p.gates = gates; p.idx = idx; p.row = row; p.w = w; p.offsets = offsets; p.meta = meta;
-  p.xp = (__nv_bfloat16*)xp; p.sync_ws = (unsigned int*)sync_ws;
-
-  int grid = lmod_num_sms();
-  if (grid > (S + 3) / 4) grid = (int)((S + 3) / 4);
-  if (grid < 1) grid = 1;
-  const int tpb = (int)((S + grid - 1) / grid);
-  size_t fixed = (size_t)E * H * 4 + (size_t)2 * S + 64;
-  LMOD_CHECK_ARG(fixed < 180 * 1024, "lmod_moe_route_scatter: S*2 + E*H*4 exceeds the shared-memory budget");
-  size_t budget = 200 * 1024 - fixed;
-  int cap = (int)(budget / ((size_t)H * 2));
-  if (cap > tpb) cap = tpb;
-  p.stage_cap = cap;
-  size_t smem = (size_t)E * H * 4 + (size_t)cap * H * 2 + (size_t)2 * S + 16;
-  static bool attr_done = false;
-  if (!attr_done) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(moe_route_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    attr_done = true;
+  p.xp = (__nv_bfloat16*)xp;
+  p.tpb = route_tpb(S);
+  p.ntiles = (int)((S + p.tpb - 1) / p.tpb);
+  LMOD_CHECK_ARG(p.tpb <= 2048, "lmod_moe_route_scatter: S = %lld is beyond the tile plan", (long long)S);
+  p.tile_cnt = ws;
+  p.tile_gsum = reinterpret_cast<float*>(ws + (size_t)p.ntiles * 2 * MAXE);
+  const size_t smem = (size_t)E * H * 4 + (size_t)p.tpb * MAXE * 4;
+  LMOD_CHECK_ARG(smem <= 200 * 1024, "lmod_moe_route_scatter: E*H*4 exceeds the shared-memory budget");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    LMOD_CUDA_OK(cudaFuncSetAttribute(moe_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
   }
-  void* args[] = {(void*)&p};
-  LMOD_CUDA_OK(cudaLaunchCooperativeKernel((const void*)moe_route_scatter_kernel, dim3(grid), dim3(RT_THREADS), args, smem,
-                                           (cudaStream_t)stream));
-  lmod_count_launch();
+  moe_gate_kernel<<<p.ntiles, RT_THREADS, smem, (cudaStream_t)stream>>>(p);
+  LMOD_LAUNCH_OK();
+  moe_seat_scatter_kernel<<<p.ntiles, RT_THREADS, 0, (cudaStream_t)stream>>>(p);
+  LMOD_LAUNCH_OK();
   return LMOD_OK;
 }
 

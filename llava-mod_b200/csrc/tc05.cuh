@@ -6,10 +6,22 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------------------------------------------
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~20 us pass) instead of spinning through
+// the issue slots the softmax warps need; the spin bound (~2.6 s) turns a protocol bug into a trap instead of a hung GPU
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase), "r"(20000u) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t phase) {
+  if (mbar_try_wait(bar, phase)) return;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, phase)) {
-    if (++spins > (1u << 22)) { printf("lmod tcgen05 kernel: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  while (!mbar_try_wait_hint(bar, phase)) {
+    if (++spins > (1u << 17)) { printf("lmod tcgen05 kernel: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
 // whole-warp wait: one lane polls the barrier, the other 31 sleep at the warp barrier (polling threads cost issue slots and power --

@@ -31,6 +31,7 @@ SIGNATURES = {
     "lmod_softmax_rows": [_P, _L, _L, _L, _I, _P, _L, _P],
     "lmod_align_loss_dense": [_P, _P, _L, _P, _L, _L, _I, _P, _P, _P],
     "lmod_moe_capacity": [_L, _I, _F, _L],
+    "lmod_moe_route_ws_elems": [_L, _I],
     "lmod_moe_route_scatter": [_P, _P, _P, _L, _L, _I, _F, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "lmod_moe_gather_combine": [_P, _P, _P, _P, _L, _L, _P, _P],
     "lmod_moe_combine_bwd": [_P, _P, _P, _P, _L, _L, _P, _P, _P],
@@ -56,12 +57,13 @@ SIGNATURES = {
     "lmod_gemm_bf16_dyn": [_P, _L, _I, _P, _L, _I, _P, _L, _L, _L, _L, _P, _I, _P, _P, _P, _P],
     "lmod_gemm_swiglu_ok": [_L, _L],
     "lmod_grouped_gemm_bf16": [_P, _L, _P, _L, _P, _L, _P, _I, _L, _L, _L, _L, _I, _I, _P],
-    "lmod_attn_fwd": [_P, _L, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P],
-    "lmod_attn_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P],
+    "lmod_attn_fwd": [_P, _L, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P, _P],
+    "lmod_attn_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P, _P, _P],
     "lmod_version": [],
     "lmod_launch_count_reset": [],
 }
-_RESTYPES = {"lmod_last_error": ctypes.c_char_p, "lmod_launch_count": c_int64, "lmod_launch_count_reset": None}
+_RESTYPES = {"lmod_last_error": ctypes.c_char_p, "lmod_launch_count": c_int64, "lmod_launch_count_reset": None,
+             "lmod_moe_route_ws_elems": c_int64}
 
 
 class LmodError(RuntimeError):

@@ -113,26 +113,27 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, ou
     return out
 
 
-_swiglu_cache = {}
-
-
-def swiglu_mlp_in(x, w_gu):
-    """Frozen-weight fast path of act_fn(gate_proj(x)) * up_proj(x): ONE GEMM whose epilogue applies SwiGLU, so the [rows, 2I] gate|up
-    activation is never written.  The kernel wants the fused weight tile-interleaved ([128 gate rows | 128 up rows] per 256); that copy is
-    built once per (frozen) weight.  Returns None when the shape does not qualify (caller falls back to GEMM + silu_mul)."""
+def swiglu_mlp_in(x, mlp):
+    """Frozen-weight fast path of act_fn(gate_proj(x)) * up_proj(x) (modeling_qwen2.py:199-200): ONE GEMM whose epilogue applies
+    SwiGLU, so the [rows, 2I] gate|up activation is never written.  The kernel wants the fused weight tile-interleaved ([128 gate
+    rows | 128 up rows] per 256); that copy is built once per FROZEN MLP module and lives on the module (it dies with it).  It is
+    rebuilt when the fused buffer was re-pointed or written through torch (load_state_dict, .data assignment); weights the optimizer
+    updates through raw pointers never qualify, because eligibility is the member Parameters' requires_grad.
+    Returns None when the module / shape does not qualify (caller falls back to GEMM + silu_mul)."""
+    w_gu = mlp.gu_weight
     x2 = _rows(x)
     M = x2.shape[0]
     N, H = w_gu.shape
     I = N // 2
-    if w_gu.requires_grad or I % 128 != 0 or not _C.lib().lmod_gemm_swiglu_ok(M, N):
+    if mlp.gate_proj.weight.requires_grad or mlp.up_proj.weight.requires_grad or I % 128 != 0 or not _C.lib().lmod_gemm_swiglu_ok(M, N):
         return None
-    key = (w_gu.data_ptr(), w_gu._version)
-    ent = _swiglu_cache.get(w_gu.data_ptr())
+    key = (w_gu.data_ptr(), w_gu._version, mlp.gate_proj.weight._version, mlp.up_proj.weight._version)
+    ent = getattr(mlp, "_swiglu_interleaved", None)
     if ent is None or ent[0] != key:
         g = w_gu[:I].view(I // 128, 128, H)
         u = w_gu[I:].view(I // 128, 128, H)
         ent = (key, torch.stack([g, u], 1).reshape(N, H).contiguous())
-        _swiglu_cache[w_gu.data_ptr()] = ent
+        mlp._swiglu_interleaved = ent
     out = torch.empty(M, I, dtype=x.dtype, device=x.device)
     call("lmod_gemm_bf16", ptr(x2), x2.stride(0), 0, ptr(ent[1]), H, 0, ptr(out), I, M, N, H, None, 2, None)
     return out
@@ -190,63 +191,81 @@ def linear(x, w, bias=None, wgrad=None, bgrad=None):
 # ---------------------------------------------------------------------------------------------------
 # attention (K7)
 # ---------------------------------------------------------------------------------------------------
-import os as _os
-
 ATTN_HEAD_DIMS = (64, 128)
-ATTN_BWD_TCGEN05 = _os.environ.get("LLAVAMOD_ATTN_BWD", "tcgen05") != "flash"
 
 
-def attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale=None, need_lse=False):
-    """Hand-written tcgen05 flash-attention forward on the fused QKV buffer [B*T, (nh+2nkv)*hd] -> [B*T, nh*hd] (+ lse [B,nh,T])."""
+def attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale=None, need_lse=False, pad=None):
+    """Hand-written tcgen05 flash-attention forward on the fused QKV buffer [B*T, (nh+2nkv)*hd] -> [B*T, nh*hd] (+ lse [B,nh,T]).
+    pad = (kv_lo, kv_hi): int32 [B] device tensors, the real key range of every batch row (padded batches), or None."""
     _need_cuda(qkv)
     out = torch.empty(B * T, nh * hd, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B, nh, T, dtype=torch.float32, device=qkv.device) if need_lse else None
+    lo, hi = pad if pad is not None else (None, None)
     call("lmod_attn_fwd", ptr(qkv), qkv.stride(0), B, T, nh, nkv, hd, 1 if causal else 0, float(scale if scale is not None else hd ** -0.5),
-         ptr(out), out.stride(0), ptr(lse) if lse is not None else None)
+         ptr(out), out.stride(0), ptr(lse) if lse is not None else None, ptr(lo), ptr(hi))
     return out, lse
 
 
 class AttnFn(Function):
-    """Qwen2SdpaAttention core (modeling_qwen2.py:713-721): our tcgen05 forward (lmod_attn_fwd) and backward (lmod_attn_bwd); dq|dk|dv
-    come back as one fused buffer.  LLAVAMOD_ATTN_BWD=flash swaps in flash-attn 2's library backward (the A/B arm of the throughput
-    report in tests/test_attn_gpu.py, not a product path)."""
+    """Qwen2SdpaAttention core (modeling_qwen2.py:713-721, 4-D mask :1035-1040): our tcgen05 forward (lmod_attn_fwd) and backward
+    (lmod_attn_bwd); dq|dk|dv come back as one fused buffer."""
 
     @staticmethod
-    def forward(ctx, qkv, B, T, nh, nkv, hd, causal, scale):
+    def forward(ctx, qkv, B, T, nh, nkv, hd, causal, scale, kv_lo, kv_hi):
         scale = float(scale if scale is not None else hd ** -0.5)
-        out, lse = attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale, need_lse=True)
-        ctx.save_for_backward(qkv, out, lse)
+        pad = (kv_lo, kv_hi) if kv_lo is not None else None
+        out, lse = attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale, need_lse=True, pad=pad)
+        ctx.save_for_backward(qkv, out, lse, kv_lo, kv_hi)
         ctx.dims = (B, T, nh, nkv, hd, causal, scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, out, lse = ctx.saved_tensors
+        qkv, out, lse, kv_lo, kv_hi = ctx.saved_tensors
         B, T, nh, nkv, hd, causal, scale = ctx.dims
-        if ATTN_BWD_TCGEN05:
-            return attention_bwd(qkv, out, _c(dout), lse, B, T, nh, nkv, hd, causal, scale), None, None, None, None, None, None, None
-        # A/B arm only: flash-attn 2's library backward fed with OUR forward's output and log-sum-exp
-        from flash_attn.flash_attn_interface import _wrapped_flash_attn_backward
-        q = qkv[:, : nh * hd].view(B, T, nh, hd)
-        k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)
-        v = qkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd)
-        dqkv = torch.empty_like(qkv)
-        dq = dqkv[:, : nh * hd].view(B, T, nh, hd)
-        dk = dqkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)
-        dv = dqkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd)
-        _wrapped_flash_attn_backward(_c(dout).view(B, T, nh, hd), q, k, v, out.view(B, T, nh, hd), lse, dq, dk, dv, 0.0, scale, bool(causal),
-                                     -1, -1, 0.0, None, False, rng_state=None)
-        return dqkv, None, None, None, None, None, None, None
+        pad = (kv_lo, kv_hi) if kv_lo is not None else None
+        return (attention_bwd(qkv, out, _c(dout), lse, B, T, nh, nkv, hd, causal, scale, pad=pad),) + (None,) * 9
 
 
-def attention_bwd(qkv, out, dout, lse, B, T, nh, nkv, hd, causal, scale):
+def attention_bwd(qkv, out, dout, lse, B, T, nh, nkv, hd, causal, scale, pad=None):
     """Hand-written tcgen05 flash-attention backward -> fused dqkv (same layout as qkv)."""
     dqkv = torch.empty_like(qkv)
     dq32 = torch.empty(B * T, nh * hd, dtype=torch.float32, device=qkv.device)
     dsum = torch.empty(B, nh, T, dtype=torch.float32, device=qkv.device)
+    lo, hi = pad if pad is not None else (None, None)
     call("lmod_attn_bwd", ptr(qkv), qkv.stride(0), ptr(out), out.stride(0), ptr(dout), dout.stride(0), ptr(lse), B, T, nh, nkv, hd,
-         1 if causal else 0, float(scale), ptr(dqkv), dqkv.stride(0), ptr(dq32), ptr(dsum))
+         1 if causal else 0, float(scale), ptr(dqkv), dqkv.stride(0), ptr(dq32), ptr(dsum), ptr(lo), ptr(hi))
     return dqkv
+
+
+def attention(qkv, B, T, nh, nkv, hd, causal=True, scale=None, pad=None):
+    """Self-attention on the fused, RoPE'd QKV buffer [B*T, (nh+2nkv)*hd] -> [B*T, nh*hd], always on the tcgen05 kernels.
+    Head dims other than 64 / 128 (the reference's tiny test shapes) are zero-padded per head to the next built width: the extra
+    q/k columns add 0 to every score and the extra v columns produce output columns that are sliced away (softmax scale = hd^-0.5 of
+    the TRUE head dim); the pad / slice are plain tensor ops, so autograd carries the gradient back to the unpadded buffer."""
+    scale = float(scale if scale is not None else hd ** -0.5)
+    if hd not in ATTN_HEAD_DIMS:
+        hp = 64 if hd < 64 else 128
+        if hd > 128:
+            raise _C.LmodError("head_dim %d > 128 is not built" % hd)
+        q3 = torch.nn.functional.pad(qkv.view(B * T, nh + 2 * nkv, hd), (0, hp - hd)).view(B * T, (nh + 2 * nkv) * hp)
+        o = attention(q3, B, T, nh, nkv, hp, causal, scale, pad)
+        return o.view(B * T, nh, hp)[:, :, :hd].reshape(B * T, nh * hd)
+    lo, hi = pad if pad is not None else (None, None)
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        return AttnFn.apply(qkv, B, T, nh, nkv, hd, causal, scale, lo, hi)
+    return attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale, pad=pad)[0]
+
+
+def pad_ranges(attention_mask):
+    """[B,T] bool mask (contiguous real tokens, right or left padded -- what the collators and the multimodal splice produce) ->
+    (kv_lo, kv_hi) int32 [B] on the device, no host sync."""
+    m = attention_mask.to(torch.int32)
+    T = m.shape[1]
+    lo = m.argmax(1).to(torch.int32)
+    hi = (T - m.flip(1).argmax(1)).to(torch.int32)
+    none = m.sum(1) == 0
+    return torch.where(none, torch.zeros_like(lo), lo).contiguous(), torch.where(none, torch.zeros_like(hi), hi).contiguous()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -483,17 +502,6 @@ def splice_embed(feats, embed_w, src, img_index, n_patches, embed_grad=None):
 # ---------------------------------------------------------------------------------------------------
 # MoE layer (DeepSpeed 0.9.5 MoE; call site llava_qwen1_5_moe.py:536-546)
 # ---------------------------------------------------------------------------------------------------
-_sync_ws = {}
-
-
-def _grid_ws(device):
-    ws = _sync_ws.get(device)
-    if ws is None:
-        ws = torch.zeros(4, dtype=torch.int32, device=device)
-        _sync_ws[device] = ws
-    return ws
-
-
 def moe_capacity(S, E, capacity_factor, min_capacity):
     return int(_C.lib().lmod_moe_capacity(S, E, float(capacity_factor), int(min_capacity)))
 
@@ -502,7 +510,7 @@ LAYOUT_COMPACT, LAYOUT_SLABS, LAYOUT_ALIGNED = 0, 1, 2
 
 
 def moe_route_scatter(x, wg, noise, capacity_factor, min_capacity, layout=LAYOUT_ALIGNED, padded=None):
-    """One cooperative launch: fp32 gate GEMV, softmax, top-1 / Gumbel top-2, stable capacity positions,
+    """Two ordinary launches (gate, seat+scatter): fp32 gate GEMV, softmax, top-1 / Gumbel top-2, stable capacity positions,
     renormalised weights, l_aux, expert offsets and the token scatter.  Returns a dict of device tensors.
     layout: 0 compact rows, 1 capacity-padded [E,C] slabs, 2 compact with 128-row aligned groups (grouped GEMM input)."""
     _need_cuda(x, wg, noise)
@@ -519,10 +527,11 @@ def moe_route_scatter(x, wg, noise, capacity_factor, min_capacity, layout=LAYOUT
         meta=torch.empty(4 + E, dtype=torch.float32, device=dev), capacity=C)
     rows = E * C if layout == LAYOUT_SLABS else (min(2 * S, E * C) + (128 * E if layout == LAYOUT_ALIGNED else 0))
     r["max_rows"] = rows
-    r["xp"] = torch.zeros(rows, H, dtype=x.dtype, device=dev)      # padding rows must be inert (zero) for the wgrad reduction
+    r["xp"] = torch.empty(rows, H, dtype=x.dtype, device=dev)      # the op zeroes the padding rows itself (inert for the wgrad reduction)
+    ws = torch.empty(int(_C.lib().lmod_moe_route_ws_elems(S, E)), dtype=torch.int32, device=dev)       # per call: safe across streams
     call("lmod_moe_route_scatter", ptr(x), ptr(wg), ptr(noise), S, H, E, float(capacity_factor), int(min_capacity), int(layout),
          ptr(r["logits"]), ptr(r["gates"]), ptr(r["idx"]), ptr(r["row"]), ptr(r["w"]), ptr(r["offsets"]), ptr(r["meta"]), ptr(r["xp"]),
-         ptr(_grid_ws(dev)))
+         ptr(ws))
     return r
 
 

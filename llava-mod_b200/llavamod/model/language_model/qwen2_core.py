@@ -3,7 +3,7 @@
 Stands in for the reference's vendored ``qwen1_5/modeling_qwen2.py`` (RMSNorm :96-110, RoPE :114-184, MLP :188-200,
 SDPA attention :644-728, decoder layer :738-812, model :932-1107) and the patched MoE forwards of
 ``llava_qwen1_5_moe.py:112-339``.  Parameter modules keep the reference's attribute / checkpoint key names;
-the arithmetic is issued through ``llavamod.kernels`` (our CUDA) plus library GEMM / attention calls.
+the arithmetic is issued through ``llavamod.kernels`` (our CUDA: GEMM, attention, norms, RoPE, MoE, loss heads).
 
 Layout decisions (B200-first):
   * q|k|v and gate|up weights live in ONE fused buffer each (one GEMM instead of three / two); the per-projection
@@ -109,6 +109,7 @@ class ParamNorm(nn.Module):
         self.weight = nn.Parameter(weight)
         self.bias = nn.Parameter(bias) if bias is not None else None
         self.variance_epsilon = eps
+        self.is_layernorm = bias is not None      # CLIP nn.LayerNorm (no weight decay in the reference's groups); Qwen2RMSNorm decays
 
 
 def _new(shape, device, dtype, std=None, ones=False):
@@ -268,7 +269,7 @@ class Qwen2Model(nn.Module):
         padded = attention_mask is not None and not bool(attention_mask.all())      # MaskInfo answers on the host (no sync)
         if hasattr(attention_mask, "mask"):
             attention_mask = attention_mask.mask
-        mask4d = _sdpa_mask(attention_mask, B, T, inputs_embeds.dtype) if padded else None
+        pad = K.pad_ranges(attention_mask) if padded else None       # per-row real key range; the attention kernels mask from it
 
         stream = inputs_embeds.reshape(B * T, H)
         branch = None                                   # pending residual-branch output (added inside the next norm)
@@ -283,7 +284,7 @@ class Qwen2Model(nn.Module):
                 x, stream = K.rmsnorm(branch, layer.input_layernorm.weight, cfg.rms_norm_eps, res=stream, wgrad=self.gview(layer.input_layernorm.weight))
             qkv = K.linear(x, at.qkv_weight, at.qkv_bias, self.gview(at.qkv_weight), self.gview(at.qkv_bias))
             qkv = K.rope_(qkv, cos, sin, pos, nh, nkv, hd)
-            attn = _attention(qkv, B, T, nh, nkv, hd, mask4d)
+            attn = K.attention(qkv, B, T, nh, nkv, hd, True, None, pad)
             branch = K.linear(attn, at.o_proj.weight, None, self.gview(at.o_proj.weight), None)
             x, stream = K.rmsnorm(branch, layer.post_attention_layernorm.weight, cfg.rms_norm_eps, res=stream,
                                   wgrad=self.gview(layer.post_attention_layernorm.weight))
@@ -308,7 +309,7 @@ class Qwen2Model(nn.Module):
             else:
                 act = None
                 if not torch.is_grad_enabled() or not (x.requires_grad or mlp.gate_proj.weight.requires_grad):
-                    act = K.swiglu_mlp_in(x, mlp.gu_weight)                  # frozen teacher: SwiGLU fused into the GEMM epilogue
+                    act = K.swiglu_mlp_in(x, mlp)                 # frozen teacher: SwiGLU fused into the GEMM epilogue
                 if act is None:
                     gu = K.linear(x, mlp.gu_weight, None, self.gview(mlp.gu_weight), None)
                     act = K.silu_mul(gu)
@@ -324,38 +325,3 @@ def gumbel_noise(shape, device):
     """deepspeed gumbel_rsample (Gumbel(0,1) via -log(-log U)); Philox stream of the current device generator."""
     u = torch.rand(shape, device=device, dtype=torch.float32).clamp_(min=1e-20, max=1.0 - 1e-7)
     return -torch.log(-torch.log(u))
-
-
-def _sdpa_mask(attention_mask, B, T, dtype):
-    """Additive [B,1,T,T] mask of _prepare_4d_causal_attention_mask_for_sdpa (modeling_qwen2.py:1035-1040) for batches
-    that contain padding; rows with no visible key are un-masked like HF's _unmask_unattended."""
-    dev = attention_mask.device
-    neg = torch.finfo(dtype).min
-    m = torch.full((T, T), neg, dtype=dtype, device=dev).triu(1)[None, None].expand(B, 1, T, T).clone()
-    m = m.masked_fill((~attention_mask.bool())[:, None, None, :], neg)
-    fully = (m == neg).all(-1, keepdim=True)
-    return m.masked_fill(fully, 0.0)
-
-
-def _attention(qkv, B, T, nh, nkv, hd, mask4d, causal=True, scale=None):
-    """K7: causal self-attention on the fused, RoPE'd QKV buffer [B*T, (nh+2nkv)*hd] -> [B*T, nh*hd].
-    head_dim 64 / 128 without padding: our tcgen05 forward (lmod_attn_fwd), flash-attn 2 library backward for the student.
-    Padded batches: SDPA with the reference's additive mask.  Other head dims: flash-attn 2 library."""
-    q = qkv[:, : nh * hd].view(B, T, nh, hd)
-    k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd)
-    v = qkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd)
-    if mask4d is None and hd in K.ATTN_HEAD_DIMS:
-        if torch.is_grad_enabled() and qkv.requires_grad:
-            return K.AttnFn.apply(qkv, B, T, nh, nkv, hd, causal, scale)
-        return K.attention_fwd(qkv, B, T, nh, nkv, hd, causal, scale)[0]
-    if mask4d is None:          # head dims the tcgen05 kernel is not built for (tiny test configs): library attention
-        from flash_attn import flash_attn_func
-        o = flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=scale, causal=causal)
-        return o.reshape(B * T, nh * hd)
-    qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
-    if nkv != nh:
-        rep = nh // nkv
-        kt = kt[:, :, None].expand(B, nkv, rep, T, hd).reshape(B, nh, T, hd)
-        vt = vt[:, :, None].expand(B, nkv, rep, T, hd).reshape(B, nh, T, hd)
-    o = torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, attn_mask=mask4d, dropout_p=0.0, scale=scale)
-    return o.transpose(1, 2).reshape(B * T, nh * hd)

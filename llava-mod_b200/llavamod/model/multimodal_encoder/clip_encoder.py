@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from ... import kernels as K
-from ..language_model.qwen2_core import ParamLinear, ParamNorm, _attention
+from ..language_model.qwen2_core import ParamLinear, ParamNorm
 
 KNOWN_TOWERS = {
     "clip-vit-large-patch14-336": dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
@@ -166,7 +166,7 @@ class CLIPVisionModel(nn.Module):
             a = layer.self_attn
             y = K.layernorm(h, layer.layer_norm1.weight, layer.layer_norm1.bias, c.layer_norm_eps)
             qkv = K.mm_nt(y, a.qkv_weight, a.qkv_bias)
-            o = _attention(qkv, n, T, nh, nh, hd, None, causal=False, scale=hd ** -0.5)
+            o = K.attention(qkv, n, T, nh, nh, hd, causal=False, scale=hd ** -0.5)
             o = K.mm_nt(o, a.out_proj.weight, a.out_proj.bias)
             K.call("lmod_add", K.ptr(h), K.ptr(o), h.numel(), K.ptr(h))
             y = K.layernorm(h, layer.layer_norm2.weight, layer.layer_norm2.bias, c.layer_norm_eps)

@@ -123,10 +123,15 @@ class DPOTrainer(BaseTrainer):
             moe_loss = torch.full_like(reward_losses, -1.0)
             losses = reward_losses
         reward_accuracies = (chosen_rewards > rejected_rewards).float()
+        # the reference logs the chosen forward's model loss (dpo_trainer.py:626): shifted CE averaged over the batch's supervised tokens
+        # (+ the model's own moe_loss, llava_qwen1_5_moe.py:431-434).  The gathered token log-probs of the fused head ARE that CE's terms.
+        n_tok = (rc["labels"][:, 1:] != self.label_pad_token_id).sum().clamp(min=1)
+        policy_chosen_sft = -policy_chosen_logps.detach().sum() / n_tok
+        if getattr(model, "is_moe", False) and len(rc["l_aux"]):
+            policy_chosen_sft = policy_chosen_sft + model.moe_loss_from(rc["l_aux"]).detach()
         outputs = {"loss": losses.detach().mean(), "loss/reward": reward_losses.detach().mean(),
                    "loss/moe_balance": moe_loss.detach().mean(),
-                   # the reference logs the chosen forward's LM loss; the fused path reports -mean token log-prob of the chosen response
-                   "loss/policy_chosen": (-policy_chosen_logps.detach()).mean(),
+                   "loss/policy_chosen": policy_chosen_sft,
                    "rewards/chosen": chosen_rewards.mean(), "rewards/rejected": rejected_rewards.mean(),
                    "rewards/accuracies": reward_accuracies.mean(), "rewards/margins": (chosen_rewards - rejected_rewards).mean(),
                    "logps/chosen": policy_chosen_logps.detach().mean(), "logps/rejected": policy_rejected_logps.detach().mean()}

@@ -50,11 +50,21 @@ def _units(model):
     return out
 
 
+def param_group_of(name, in_layernorm, projector_lr_set):
+    """The reference's optimizer groups (align_trainer.py:341-398, same in dpo_trainer.py:348 / llava_trainer.py:167):
+    decay = every parameter that is not inside an nn.LayerNorm (Qwen2RMSNorm is NOT in ALL_LAYERNORM_LAYERS, so RMSNorm weights decay)
+    and whose name does not contain "bias"; with --mm_projector_lr the names containing "mm_projector" form their own two groups.
+    -> (is_projector_group, no_decay)"""
+    no_decay = in_layernorm or ("bias" in name)
+    return (bool(projector_lr_set and "mm_projector" in name), bool(no_decay))
+
+
 class TrainState:
     def __init__(self, model, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
-                 process_group=None):
+                 process_group=None, mm_projector_lr=None):
         self.model = model
         self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.mm_projector_lr = mm_projector_lr
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
@@ -65,6 +75,9 @@ class TrainState:
         if orphans:
             raise NotImplementedError("trainable vision-tower parameters (%s ...): the tower's backward is not built -- the reference's "
                                       "recipes keep it frozen" % orphans[0])
+        names = {id(p_): n for n, p_ in model.named_parameters()}
+        ln_params = {id(p_) for mod in model.modules() if isinstance(mod, torch.nn.LayerNorm) or getattr(mod, "is_layernorm", False)
+                     for p_ in mod.parameters(recurse=False)}
         u16, u32 = [], []
         for storage, members in _units(model):
             rg = [m.requires_grad for m in members]
@@ -73,7 +86,14 @@ class TrainState:
             if not all(rg):
                 raise NotImplementedError("a fused buffer with mixed frozen/trainable members (e.g. only gate_proj of gate|up) "
                                           "is not supported; train or freeze q/k/v and gate/up together")
-            (u32 if storage.dtype == torch.float32 else u16).append((storage, members))
+            keys = {param_group_of(names.get(id(m), ""), id(m) in ln_params, mm_projector_lr is not None) for m in members}
+            if len(keys) != 1:
+                raise NotImplementedError("a fused buffer whose members fall into different optimizer groups")
+            (u32 if storage.dtype == torch.float32 else u16).append((storage, members, keys.pop()))
+        # units of one optimizer group (decay / no-decay x projector-lr) are laid out contiguously, so a group is ONE slice of the arenas
+        u16.sort(key=lambda u: u[2])
+        u32.sort(key=lambda u: u[2])
+        self.segments = {}
         self.n16 = self._pack(u16, torch.bfloat16, dev, "16")
         self.n32 = self._pack(u32, torch.float32, dev, "32")
         self.master = self.w16.float() if self.n16 else None
@@ -95,10 +115,16 @@ class TrainState:
         self.num_trainable = self.n16 + self.n32
 
     def _pack(self, units, dtype, dev, tag):
-        off, plan = 0, []
-        for storage, members in units:
+        off, plan, segs = 0, [], []
+        for storage, members, key in units:
             plan.append((storage, members, off))
-            off += (storage.numel() + ALIGN - 1) // ALIGN * ALIGN
+            nxt = off + (storage.numel() + ALIGN - 1) // ALIGN * ALIGN
+            if segs and segs[-1][0] == key:
+                segs[-1][2] = nxt
+            else:
+                segs.append([key, off, nxt])
+            off = nxt
+        self.segments[tag] = [(k, a, b) for k, a, b in segs]
         w = torch.zeros(max(off, 1), dtype=dtype, device=dev)
         g = torch.zeros(max(off, 1), dtype=dtype, device=dev)
         views = getattr(self, "_views", [])
@@ -132,6 +158,11 @@ class TrainState:
         if self.n32:
             self.g32.zero_()
 
+    def refresh_master(self):
+        """fp32 master copy <- current bf16 weights (after a checkpoint / adaptor was loaded into the model)."""
+        if self.n16:
+            self.master.copy_(self.w16.float())
+
     def allreduce_grads(self):
         """The one exchange step of data parallelism: sum the flat student gradient buffers over NVLink (NCCL)."""
         if self.world > 1:
@@ -155,12 +186,17 @@ class TrainState:
                 K.sumsq_(self.g32, self.gnorm_sq)
         gn = self.gnorm_sq if use_clip else None
         mx = float(self.max_grad_norm) if use_clip else 0.0
-        if self.n16:
-            K.adamw_(self.master, self.m16, self.v16, self.g16, self.w16, lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                     self.step_count, gn, mx, grad_scale)
-        if self.n32:
-            K.adamw_(self.w32, self.m32, self.v32, self.g32, None, lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                     self.step_count, gn, mx, grad_scale)
+        # one fused AdamW launch per optimizer group (a contiguous slice of the arenas); the clip coefficient is global (one norm over
+        # every group, as torch.nn.utils.clip_grad_norm_ over all parameters), the projector group follows the same schedule scaled to its
+        # own base LR (HF schedulers multiply each group's initial lr by the same lambda)
+        for (is_proj, no_decay), a, b in (self.segments["16"] if self.n16 else []):
+            g_lr = lr * (self.mm_projector_lr / self.lr) if (is_proj and self.lr) else lr
+            K.adamw_(self.master[a:b], self.m16[a:b], self.v16[a:b], self.g16[a:b], self.w16[a:b], g_lr, self.betas[0], self.betas[1], self.eps,
+                     0.0 if no_decay else self.wd, self.step_count, gn, mx, grad_scale)
+        for (is_proj, no_decay), a, b in (self.segments["32"] if self.n32 else []):
+            g_lr = lr * (self.mm_projector_lr / self.lr) if (is_proj and self.lr) else lr
+            K.adamw_(self.w32[a:b], self.m32[a:b], self.v32[a:b], self.g32[a:b], None, g_lr, self.betas[0], self.betas[1], self.eps,
+                     0.0 if no_decay else self.wd, self.step_count, gn, mx, grad_scale)
 
     def grad_norm(self, grad_scale=1.0):
         return float(torch.sqrt(self.gnorm_sq)[0]) * grad_scale

@@ -98,3 +98,23 @@ class RankShard(Sampler):
         for rnd in range(self._rounds()):
             start = (rnd * w + self.rank) * b
             yield from order[start: start + b]
+
+
+class EpochSeededRandomSampler(torch.utils.data.Sampler):
+    """Single-process counterpart of DistributedSampler(shuffle=True, seed): the permutation of epoch e is a function of (seed, e)
+    alone, so a run resumed from checkpoint-N walks the same batches the uninterrupted run would (HF Trainer reaches the same goal by
+    re-seeding and skipping)."""
+
+    def __init__(self, data_source, seed=42):
+        self.n, self.seed, self.epoch = len(data_source), int(seed), 0
+
+    def set_epoch(self, epoch):
+        self.epoch = int(epoch)
+
+    def __iter__(self):
+        g = torch.Generator()
+        g.manual_seed(self.seed + self.epoch)
+        return iter(torch.randperm(self.n, generator=g).tolist())
+
+    def __len__(self):
+        return self.n

@@ -58,21 +58,24 @@ class BaseTrainer:
         # CUDA graphs: the forward+backward of a micro-batch is captured once per input signature and replayed, which
         # removes the per-launch host cost (~1000 launches per micro-batch) -- "CUDA streams and graphs instead of a tracing compiler"
         self.use_cuda_graphs = bool(int(os.environ.get("LLAVAMOD_CUDA_GRAPHS", "1")))
-        self._graphs = {}
+        self._graphs = {}                    # signature -> captured graph (LRU, bounded) ; or {"warm": n} while still eager
+        # real data (per_device_train_batch_size 1, variable lengths) produces a new signature per distinct length: every captured graph
+        # pins its activations, so the cache is bounded (least-recently-used graph dropped) and all graphs share ONE memory pool
+        self.max_graphs = int(os.environ.get("LLAVAMOD_MAX_GRAPHS", "6"))
+        self._graph_pool = None
         self._suppress_store = False
         self.graph_replayed_launches = 0     # liblmod kernels executed through graph replays (not seen by the host-side counter)
 
     # ---- optimizer ---------------------------------------------------------------------------------------
     def create_optimizer(self):
-        """One AdamW group over every trainable parameter (reference: align_trainer.py:326-434 builds decay / no-decay /
-        projector-lr groups and MoE param groups; with --weight_decay 0. and no --mm_projector_lr, as in the distillation
-        shells, they collapse to this)."""
+        """Fused AdamW over the flat arenas with the reference's parameter groups (align_trainer.py:326-434): decay / no-decay (names
+        containing "bias", nn.LayerNorm parameters) and, with --mm_projector_lr, the projector's own LR groups -- each a contiguous slice
+        of the arenas (engine.TrainState).  DeepSpeed's split into MoE expert groups changes no hyper-parameter and is not mirrored."""
         if self.optimizer is None:
             a = self.args
-            if getattr(a, "mm_projector_lr", None) is not None:
-                raise NotImplementedError("--mm_projector_lr (separate projector LR group) is not used by the distillation shells")
             self.optimizer = TrainState(self.model, lr=a.learning_rate, betas=(a.adam_beta1, a.adam_beta2), eps=a.adam_epsilon,
-                                        weight_decay=a.weight_decay, max_grad_norm=a.max_grad_norm)
+                                        weight_decay=a.weight_decay, max_grad_norm=a.max_grad_norm,
+                                        mm_projector_lr=getattr(a, "mm_projector_lr", None))
         return self.optimizer
 
     def current_lr(self):
@@ -129,21 +132,31 @@ class BaseTrainer:
         if sig is None:
             return None
         pipelined = isinstance(sig, tuple) and sig[-1] == "pipelined"
-        ent = self._graphs.get(sig)
+        ent = self._graphs.pop(sig, None)                # re-inserted below: dict order = recency
         if ent is None:
-            ent = self._graphs[sig] = {"warm": 0}
+            ent = {"warm": 0}
+            if len(self._graphs) > 4096:                 # rarely seen signatures never reach capture; forget the oldest counters
+                for k in [k for k, v in self._graphs.items() if "graph" not in v][:2048]:
+                    del self._graphs[k]
+        self._graphs[sig] = ent
         if "graph" not in ent:
             ent["warm"] += 1
             if ent["warm"] <= 2:                         # eager warm-up (lazy init, autotune, workspace allocation)
                 return None
+            captured = [k for k, v in self._graphs.items() if "graph" in v]
+            while len(captured) >= max(1, self.max_graphs):      # drop the least recently used graph with its static buffers
+                old = self._graphs.pop(captured.pop(0))
+                old.clear()
             static = self._graph_static_inputs(inputs, None, next_inputs, pipelined) if pipelined else self._graph_static_inputs(inputs, None)
             torch.cuda.synchronize()
             from .. import _C
             g = torch.cuda.CUDAGraph()
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
             self._suppress_store = True
             n0 = _C.launch_count()
             try:
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, pool=self._graph_pool):
                     loss, outputs = self.compute_loss(model, static, return_outputs=True)
                     loss.backward()
                     if hasattr(self, "_graph_epilogue"):
@@ -196,26 +209,40 @@ class BaseTrainer:
             sampler = RankShard(grouped, a.per_device_train_batch_size, self.rank, self.world_size)
             return DataLoader(self.train_dataset, batch_size=a.per_device_train_batch_size, sampler=sampler, collate_fn=self.data_collator,
                               num_workers=a.dataloader_num_workers, pin_memory=True, drop_last=True)
-        sampler = DistributedSampler(self.train_dataset, shuffle=True, seed=self.args.seed) if self.world_size > 1 else None
+        if self.world_size > 1:
+            sampler = DistributedSampler(self.train_dataset, shuffle=True, seed=self.args.seed)
+        else:
+            from .sampler import EpochSeededRandomSampler       # order is a function of (seed, epoch): a resumed run sees the same batches
+            sampler = EpochSeededRandomSampler(self.train_dataset, seed=self.args.seed)
         return DataLoader(self.train_dataset, batch_size=self.args.per_device_train_batch_size, sampler=sampler,
-                          shuffle=(sampler is None), collate_fn=self.data_collator,
-                          num_workers=self.args.dataloader_num_workers, pin_memory=True, drop_last=True)
+                          collate_fn=self.data_collator, num_workers=self.args.dataloader_num_workers, pin_memory=True, drop_last=True)
 
     def train(self, resume_from_checkpoint=None):
         a = self.args
         dl = self.get_train_dataloader()
         steps_per_epoch = max(1, len(dl) // a.gradient_accumulation_steps)
         self._total_steps = a.max_steps if a.max_steps > 0 else int(steps_per_epoch * a.num_train_epochs)
+        rng = None
         if resume_from_checkpoint:
-            self._load_checkpoint(resume_from_checkpoint)
+            rng = self._load_checkpoint(resume_from_checkpoint)
+        # resume where the interrupted run stopped (HF Trainer: epochs_trained / skip_first_batches): same epoch, the micro-batches the
+        # finished optimizer steps consumed are skipped, and the RNG streams (router Gumbel noise, samplers) continue from the saved state
+        epoch = self.state.global_step // steps_per_epoch
+        skip = (self.state.global_step % steps_per_epoch) * a.gradient_accumulation_steps
         t0 = time.time()
         tr_loss, n_loss = 0.0, 0
-        done = False
-        epoch = 0
+        done = self.state.global_step >= self._total_steps
         while not done:
             if hasattr(dl.sampler, "set_epoch"):
                 dl.sampler.set_epoch(epoch)
-            for batch, nxt in _with_lookahead(dl):
+            it = iter(dl)
+            for _ in range(skip):
+                next(it, None)
+            skip = 0
+            if rng is not None:                          # after the skipped batches were drawn: the loop below continues the saved streams
+                self._restore_rng(rng)
+                rng = None
+            for batch, nxt in _with_lookahead(it):
                 before = self.state.global_step
                 loss = self.training_step(self.model, batch, nxt)     # look-ahead: the frozen teacher runs one micro-batch ahead
                 tr_loss += float(loss); n_loss += 1
@@ -265,6 +292,7 @@ class BaseTrainer:
                             "v32": opt.v32, "step_count": opt.step_count}, os.path.join(d, "optimizer.pt"))
             with open(os.path.join(d, "trainer_state.json"), "w") as f:
                 json.dump({"global_step": self.state.global_step, "log_history": self.state.log_history}, f)
+            torch.save(self._rng_state(), os.path.join(d, "rng_state.pth"))
             lim = self.args.save_total_limit
             if lim:
                 cks = sorted(glob.glob(os.path.join(self._get_output_dir(trial), "checkpoint-*")),
@@ -275,18 +303,49 @@ class BaseTrainer:
         if self.world_size > 1:
             dist.barrier()
 
+    def _rng_state(self):
+        st = {"cpu": torch.get_rng_state()}
+        if torch.cuda.is_available():
+            st["cuda"] = torch.cuda.get_rng_state()
+        return st
+
+    def _restore_rng(self, st):
+        torch.set_rng_state(st["cpu"].cpu())
+        if "cuda" in st and torch.cuda.is_available():
+            torch.cuda.set_rng_state(st["cuda"].cpu())
+
     def _load_checkpoint(self, d):
+        """Restores weights, optimizer arenas, step count and returns the saved RNG state (or None).  Adaptor-only checkpoints
+        (mm_projector.bin, written under --tune_mm_mlp_adapter) carry no optimizer state: the weights are loaded and the optimizer
+        starts fresh, as the reference does when it re-reads --pretrain_mm_mlp_adapter."""
         from ..model.builder_io import load_into, load_state_dict_files
         if d is True:
             cks = sorted(glob.glob(os.path.join(self.args.output_dir, "checkpoint-*")),
                          key=lambda p: int(re.findall(r"checkpoint-(\d+)", p)[-1]))
             d = cks[-1]
         opt = self.create_optimizer()
-        load_into(self.model, load_state_dict_files(d), strict=False)
-        st = torch.load(os.path.join(d, "optimizer.pt"), map_location=self.model.device, weights_only=True)
-        for k in ("master", "m16", "v16", "m32", "v32"):
-            if st.get(k) is not None and getattr(opt, k) is not None:
-                getattr(opt, k).copy_(st[k])
-        opt.step_count = st["step_count"]
-        with open(os.path.join(d, "trainer_state.json")) as f:
-            self.state.global_step = json.load(f)["global_step"]
+        adaptor = os.path.join(d, "mm_projector.bin")
+        if os.path.exists(adaptor) and not glob.glob(os.path.join(d, "pytorch_model*.bin")) and not glob.glob(os.path.join(d, "*.safetensors")):
+            sd = torch.load(adaptor, map_location="cpu", weights_only=True)
+            load_into(self.model, sd, strict=False)
+        else:
+            load_into(self.model, load_state_dict_files(d), strict=False)
+        opt.refresh_master()                                 # fp32 master copy follows the weights just loaded
+        op = os.path.join(d, "optimizer.pt")
+        if os.path.exists(op):
+            st = torch.load(op, map_location=self.model.device, weights_only=True)
+            for k in ("master", "m16", "v16", "m32", "v32"):
+                if st.get(k) is not None and getattr(opt, k) is not None:
+                    getattr(opt, k).copy_(st[k])
+            opt.step_count = st["step_count"]
+        else:
+            print("[resume] %s has no optimizer.pt (adaptor-only checkpoint): weights restored, optimizer state starts fresh" % d, flush=True)
+        m = re.findall(r"checkpoint-(\d+)", d)
+        ts = os.path.join(d, "trainer_state.json")
+        if os.path.exists(ts):
+            with open(ts) as f:
+                self.state.global_step = json.load(f)["global_step"]
+        elif m:
+            self.state.global_step = int(m[-1])
+        rp = os.path.join(d, "rng_state.pth")
+        return torch.load(rp, map_location="cpu", weights_only=True) if os.path.exists(rp) else None

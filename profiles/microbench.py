@@ -15,12 +15,24 @@ REPS = int(os.environ.get("REPS", "1"))
 
 
 def timed(name, fn, work, unit):
+    """REPS back-to-back launches replayed from a CUDA graph (as the training step runs them): device time per call, no host launch /
+    allocation cost in the number."""
     fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        fn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(REPS):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(REPS):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / REPS
@@ -94,7 +106,17 @@ def main():
     x = torch.randn(T, 1024, device=dev).to(torch.bfloat16)
     wg = torch.randn(4, 1024, device=dev) * 0.1
     noise = torch.randn(T, 4, device=dev)
-    timed("moe_route_scatter S2048 H1024 E4", lambda: K.moe_route_scatter(x, wg, noise, 1.5, 0), T * 3 * 1024 * 2, "GB/s")
+    timed("moe_route_scatter S2048 H1024 E4 (12288 B/token: route+scatter+combine share)", lambda: K.moe_route_scatter(x, wg, noise, 1.5, 0), T * 3 * 1024 * 2, "GB/s")
+    r = K.moe_route_scatter(x, wg, noise, 1.5, 0)
+    y = torch.randn(r["xp"].shape, device=dev).to(torch.bfloat16)
+    timed("moe_gather_combine S2048 H1024", lambda: K.moe_gather_combine(y, r["row"], r["w"], x), T * 4 * 1024 * 2, "GB/s")
+    # attention backward
+    for (B, Tt, nh, hd) in [(1, T, 16, 64), (1, T, 16, 128)]:
+        qkv = torch.randn(B * Tt, 3 * nh * hd, device=dev).to(torch.bfloat16)
+        out, lse = K.attention_fwd(qkv, B, Tt, nh, nh, hd, True, need_lse=True)
+        go = torch.randn_like(out)
+        timed("attn bwd T%d nh%d hd%d" % (Tt, nh, hd), lambda: K.attention_bwd(qkv, out, go, lse, B, Tt, nh, nh, hd, True, hd ** -0.5),
+              2.5 * 4.0 * B * nh * Tt * Tt * hd * 0.5, "TFLOP/s")
 
 
 if __name__ == "__main__":

@@ -64,12 +64,77 @@ def test_attn_fn_default_backward_path():
     B, T, nh, nkv, hd = 2, 384, 4, 2, 64
     g = torch.Generator(device="cuda").manual_seed(0)
     qkv = torch.randn(B * T, (nh + 2 * nkv) * hd, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True)
-    out = K.AttnFn.apply(qkv, B, T, nh, nkv, hd, True, None)
+    out = K.AttnFn.apply(qkv, B, T, nh, nkv, hd, True, None, None, None)
     go = torch.randn(B * T, nh * hd, device="cuda", generator=g).to(torch.bfloat16)
     out.backward(go)
     x = qkv.detach().float().requires_grad_(True)
     ref, _ = ref_attn(x, B, T, nh, nkv, hd, True, hd ** -0.5)
     ref.backward(go.float())
+    assert (qkv.grad.float() - x.grad).norm().item() / x.grad.norm().item() < 2e-2
+
+
+def ref_attn_padded(qkv, B, T, nh, nkv, hd, scale, keep):
+    """fp32 attention under the reference's additive 4-D mask (modeling_qwen2.py:1035-1040): causal + key padding, rows with no
+    visible key un-masked (HF _unmask_unattended).  keep [B,T] bool."""
+    q = qkv[:, : nh * hd].view(B, T, nh, hd).transpose(1, 2).float()
+    k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, T, nkv, hd).transpose(1, 2).float().repeat_interleave(nh // nkv, 1)
+    v = qkv[:, (nh + nkv) * hd:].view(B, T, nkv, hd).transpose(1, 2).float().repeat_interleave(nh // nkv, 1)
+    s = (q @ k.transpose(-1, -2)) * scale
+    vis = torch.ones(T, T, dtype=torch.bool, device=s.device).tril()[None, None] & keep[:, None, None, :]
+    vis = vis | ~vis.any(-1, keepdim=True)
+    s = s.masked_fill(~vis, float("-inf"))
+    o = torch.softmax(s, -1) @ v
+    return o.transpose(1, 2).reshape(B * T, nh * hd), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("hd,T,side", [(64, 200, "right"), (128, 333, "right"), (64, 300, "left"), (128, 130, "left"), (64, 64, "right")])
+def test_attn_padded_batch_fwd_bwd_matches_masked_reference(hd, T, side):
+    """Padded batches stay on the tcgen05 kernels (per-row key range): forward, LSE and dq|dk|dv against fp32 attention under the
+    reference's 4-D mask, incl. the un-masked rows in front of a left-padded sequence and a sample that is all padding."""
+    from llavamod import kernels as K
+    B, nh, nkv = 4, 4, 2
+    g = torch.Generator(device="cuda").manual_seed(T + hd)
+    lens = [T, max(1, T // 3), T - 5, 0]
+    keep = torch.zeros(B, T, dtype=torch.bool, device="cuda")
+    for b, n in enumerate(lens):
+        if n:
+            if side == "right":
+                keep[b, :n] = True
+            else:
+                keep[b, T - n:] = True
+    qkv = torch.randn(B * T, (nh + 2 * nkv) * hd, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True)
+    go = torch.randn(B * T, nh * hd, device="cuda", generator=g).to(torch.bfloat16)
+    pad = K.pad_ranges(keep)
+    out, lse = K.attention_fwd(qkv.detach(), B, T, nh, nkv, hd, True, hd ** -0.5, need_lse=True, pad=pad)
+    dqkv = K.attention_bwd(qkv.detach(), out, go, lse, B, T, nh, nkv, hd, True, hd ** -0.5, pad=pad)
+    torch.cuda.synchronize()
+    x = qkv.detach().float().requires_grad_(True)
+    ref, ref_lse = ref_attn_padded(x, B, T, nh, nkv, hd, hd ** -0.5, keep)
+    ref.backward(go.float())
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-3
+    torch.testing.assert_close(lse, ref_lse, rtol=1e-3, atol=1e-3)
+    for name, sl in (("dq", slice(0, nh * hd)), ("dk", slice(nh * hd, (nh + nkv) * hd)), ("dv", slice((nh + nkv) * hd, None))):
+        a, r = dqkv[:, sl].float(), x.grad[:, sl]
+        assert (a - r).norm().item() / r.norm().item() < 2e-2, name
+    # the un-padded path and the padded path agree bit for bit on a sample without padding
+    out0, _ = K.attention_fwd(qkv.detach()[:T], 1, T, nh, nkv, hd, True, hd ** -0.5)
+    assert torch.equal(out0, out[:T])
+
+
+@pytest.mark.parametrize("hd", [32, 16, 96])
+def test_attn_other_head_dims_run_on_the_same_kernels(hd):
+    """head dims that are not 64 / 128 (the reference's tiny test shapes) are zero-padded per head, not sent to a library."""
+    from llavamod import kernels as K
+    B, T, nh, nkv = 2, 150, 4, 2
+    g = torch.Generator(device="cuda").manual_seed(hd)
+    qkv = torch.randn(B * T, (nh + 2 * nkv) * hd, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True)
+    go = torch.randn(B * T, nh * hd, device="cuda", generator=g).to(torch.bfloat16)
+    out = K.attention(qkv, B, T, nh, nkv, hd, True)
+    out.backward(go)
+    x = qkv.detach().float().requires_grad_(True)
+    ref, _ = ref_attn(x, B, T, nh, nkv, hd, True, hd ** -0.5)
+    ref.backward(go.float())
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-3
     assert (qkv.grad.float() - x.grad).norm().item() / x.grad.norm().item() < 2e-2
 
 

@@ -61,10 +61,20 @@ def test_gemm_fused_swiglu_epilogue():
     g = torch.Generator(device="cuda").manual_seed(9)
     x = torch.randn(M, H, device="cuda", generator=g).to(torch.bfloat16)
     w = (torch.randn(2 * I, H, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
-    fused = Kk.swiglu_mlp_in(x, w)
+    from llavamod.model.language_model.qwen2_core import Qwen2Config, Qwen2MLP
+    cfg = Qwen2Config(hidden_size=H, intermediate_size=I)
+    mlp = Qwen2MLP(cfg, "cuda", torch.bfloat16, gu=w, dn=torch.zeros(H, I, device="cuda", dtype=torch.bfloat16))
+    assert Kk.swiglu_mlp_in(x, mlp) is None                   # trainable weights never take the cached-copy path
+    for p_ in mlp.parameters():
+        p_.requires_grad = False
+    fused = Kk.swiglu_mlp_in(x, mlp)
     assert fused is not None
     two_step = Kk.silu_mul(Kk.gemm(x, w))
     assert torch.equal(fused, two_step)
+    # the interleaved copy follows the weights: an in-place update through torch (load_state_dict path) rebuilds it
+    with torch.no_grad():
+        mlp.gate_proj.weight.mul_(0.5)
+    assert torch.equal(Kk.swiglu_mlp_in(x, mlp), Kk.silu_mul(Kk.gemm(x, w)))
     ref = torch.nn.functional.silu(x.float() @ w[:I].float().t()) * (x.float() @ w[I:].float().t())
     # vs the un-rounded fp32 formula: gate, up and silu(gate) are each rounded to bf16 on the way (as in the reference's bf16 modules)
     err = (fused.float() - ref).abs()

@@ -154,7 +154,8 @@ def test_dense_compat_kernels():
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("S,H,E,cf,padded", [(64, 128, 4, 1.5, True), (333, 256, 4, 1.0, False), (2048, 1024, 4, 1.5, True),
                                              (500, 128, 8, 0.5, False), (16, 64, 2, 2.0, True), (2048, 1024, 4, 1.5, "aligned"),
-                                             (700, 128, 4, 0.75, "aligned")])
+                                             (700, 128, 4, 0.75, "aligned"), (4096, 2048, 8, 1.5, "aligned"), (20001, 64, 4, 1.25, "aligned"),
+                                             (17, 64, 4, 1.5, False)])
 def test_route_scatter_bit_exact(S, H, E, cf, padded):
     from llavamod import kernels as K
     g = torch.Generator().manual_seed(S + E)
@@ -190,7 +191,8 @@ def test_route_scatter_bit_exact(S, H, E, cf, padded):
         assert int(meta[2].item()) == int(cnt.sum()) and int(meta[3].item()) == int(off[-1]) and off[-1] <= r["xp"].shape[0]
         unused = torch.ones(r["xp"].shape[0], dtype=torch.bool)
         unused[torch.cat([row[:, 0][keep1], row[:, 1][keep2]])] = False
-        assert bool((r["xp"].cpu()[unused] == 0).all())                  # padding rows stay zero (inert in the grouped wgrad)
+        unused[int(off[-1]):] = False                                    # rows past offsets[E] are never read by a GEMM (uninitialised)
+        assert bool((r["xp"].cpu()[unused] == 0).all())                  # the op zeroes the alignment rows (inert in the grouped wgrad)
     elif padded:
         assert torch.equal(off, torch.arange(E + 1) * C)
     else:
@@ -202,6 +204,29 @@ def test_route_scatter_bit_exact(S, H, E, cf, padded):
     # every kept row is written exactly once
     used = torch.cat([row[:, 0][keep1], row[:, 1][keep2]])
     assert used.unique().numel() == used.numel()
+
+
+def test_route_scatter_concurrent_streams_do_not_share_state():
+    """Two routers in flight on two streams (student on the main stream, a sparse teacher on the side stream): the op owns its scratch
+    per call, so both produce what they produce alone (the round-1 kernel shared one grid-barrier word per device)."""
+    from llavamod import kernels as K
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(2048, 1024, generator=g).to(torch.bfloat16).to(dev()) for _ in range(2)]
+    wg = (torch.randn(4, 1024, generator=g) * 0.2).to(dev())
+    noise = R.gumbel_noise((2048, 4), g).to(dev())
+    alone = [K.moe_route_scatter(x, wg, noise, 1.5, 0) for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    both = [None, None]
+    for rep in range(20):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                both[i] = K.moe_route_scatter(xs[i], wg, noise, 1.5, 0)
+        torch.cuda.synchronize()
+        for a, b in zip(alone, both):
+            n = int(a["offsets"][-1])
+            assert torch.equal(a["row"], b["row"]) and torch.equal(a["offsets"], b["offsets"]) and torch.equal(a["xp"][:n], b["xp"][:n])
+            assert torch.equal(a["meta"], b["meta"]) and torch.equal(a["w"], b["w"])
 
 
 def test_moe_layer_forward_backward_vs_oracle():
