@@ -7,7 +7,8 @@
 // One CTA = one (batch, head, 128-query block); two CTAs are co-resident per SM so one CTA's softmax overlaps the other's MMAs.
 // Padded batches (right or left padding, per-row key range [kv_lo, kv_hi)) run on the same kernel: the CTA walks only the key blocks
 // its rows can see and masks per element; rows with no visible key are un-masked as in the reference's 4-D mask.
-//   warp 0 lane 0 : TMA producer -- Q tile once, K/V blocks of 64 keys through a 2-stage 128B-swizzled ring
+//   warp 0 lane 0 / lane 1 : TMA producers -- Q tile once and the K ring / the V ring (blocks of 64 keys, 128B swizzle; separate rings so K
+//                                   runs NST blocks ahead of its use)
 //   warp 1 lane 0 : MMA issuer   -- S_j = Q K_j^T (SS, M=128 N=64 K=16 x hd/16) into one of two S buffers in TMEM;
 //                                   O += P_j V_j (TS: A = P_j read from TMEM, B = V_j MN-major from smem, N = hd)
 //   warps 2..9    : softmax      -- two threads per query row (TMEM lane = row; warps 2-5 take key columns 0-31 of each block, warps 6-9
@@ -70,14 +71,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   constexpr int Q_BYTES = BQ * HD * 2;
   constexpr int K_BYTES = BKV * HD * 2, V_BYTES = BKV * HD * 2;
   constexpr int TMEM_COLS = (2 * BKV + HD <= 256) ? 256 : 512;
+  // K and V blocks ride in SEPARATE rings with their own full / empty barriers: a K slot is free again as soon as S = Q K^T of its block
+  // has been computed (long before the block's P V), so the K of block j+NST is in flight NST iterations ahead of its use and the
+  // L2 / HBM latency of the loads stays off the per-block critical path (with one K|V ring of two stages it was ON it: a block's loads
+  // could only be issued after the P V of block j-2, i.e. one softmax before they were needed).  hd 64: 4 stages; hd 128: 2 (shared memory)
+  constexpr int NST = (HD == 64) ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], p_full[2], pv_done;
+  __shared__ __align__(8) uint64_t q_full, k_full[NST], k_empty[NST], v_full[NST], v_empty[NST], s_full[2], p_full[2], pv_done;
   __shared__ uint32_t tmem_slot;
   __shared__ float xmax[2][2][BQ], xsum[2][BQ];        // row-max exchange (per S buffer, per column group) and final row-sum exchange
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + Q_BYTES;                      // stage s: K at sKV + s*(K+V), V right after
+  uint8_t* sK0 = smem + Q_BYTES;                      // K stage s at sK0 + s*K_BYTES
+  uint8_t* sV0 = sK0 + NST * K_BYTES;                 // V stage s at sV0 + s*V_BYTES
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // heavier (later) causal query blocks first
@@ -99,7 +106,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); }
     mbar_init(&pv_done, 1);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_q) : "memory");
@@ -113,54 +121,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   const uint32_t tS0 = tmem, tO = tmem + 2 * BKV;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: Q once, then the K ring =====================
     mbar_expect_tx(&q_full, Q_BYTES);
 #pragma unroll
     for (int i = 0; i < KSUB; ++i) tma_load_2d(sQ + i * (BQ * 128), &tma_q, col_q + 64 * i, row_base + q0, &q_full);
     for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      mbar_wait_bounded(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-      uint8_t* sK = sKV + s * (K_BYTES + V_BYTES);
-      uint8_t* sV = sK + K_BYTES;
-      mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+      const int s = j % NST;
+      mbar_wait_bounded(&k_empty[s], ((j / NST) & 1) ^ 1);
+      uint8_t* sK = sK0 + s * K_BYTES;
+      mbar_expect_tx(&k_full[s], K_BYTES);
 #pragma unroll
-      for (int i = 0; i < KSUB; ++i) {
-        tma_load_2d(sK + i * (BKV * 128), &tma_kv, col_k + 64 * i, row_base + (jb + j) * BKV, &kv_full[s]);
-        tma_load_2d(sV + i * (BKV * 128), &tma_kv, col_v + 64 * i, row_base + (jb + j) * BKV, &kv_full[s]);
-      }
+      for (int i = 0; i < KSUB; ++i) tma_load_2d(sK + i * (BKV * 128), &tma_kv, col_k + 64 * i, row_base + (jb + j) * BKV, &k_full[s]);
+    }
+  } else if (warp == 0 && lane == 1) {
+    // ===================== TMA producer: the V ring =====================
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j % NST;
+      mbar_wait_bounded(&v_empty[s], ((j / NST) & 1) ^ 1);
+      uint8_t* sV = sV0 + s * V_BYTES;
+      mbar_expect_tx(&v_full[s], V_BYTES);
+#pragma unroll
+      for (int i = 0; i < KSUB; ++i) tma_load_2d(sV + i * (BKV * 128), &tma_kv, col_v + 64 * i, row_base + (jb + j) * BKV, &v_full[s]);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     const uint32_t idesc_qk = attn_idesc(BKV, false), idesc_pv = attn_idesc(HD, true);
     const uint32_t aQ = smem_u32(sQ);
     auto issue_qk = [&](int j) {
-      const int s = j & 1;
-      mbar_wait_bounded(&kv_full[s], (j >> 1) & 1);
+      const int s = j % NST, sb = j & 1;
+      mbar_wait_bounded(&k_full[s], (j / NST) & 1);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sKV + s * (K_BYTES + V_BYTES));
+      const uint32_t aK = smem_u32(sK0 + s * K_BYTES);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k) {
         const uint64_t da = smem_desc(aQ + (k / 4) * (BQ * 128) + (k % 4) * 32, 16, 1024);
         const uint64_t db = smem_desc(aK + (k / 4) * (BKV * 128) + (k % 4) * 32, 16, 1024);
-        umma_f16(tS0 + s * BKV, da, db, idesc_qk, k > 0 ? 1u : 0u);
+        umma_f16(tS0 + sb * BKV, da, db, idesc_qk, k > 0 ? 1u : 0u);
       }
-      umma_commit(&s_full[s]);
+      umma_commit(&k_empty[s]);                       // the K slot is reusable as soon as these MMAs have read it
+      umma_commit(&s_full[sb]);
     };
     mbar_wait_bounded(&q_full, 0);
     issue_qk(0);
     for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
+      const int s = j % NST, sb = j & 1;
       if (j + 1 < nblk) issue_qk(j + 1);              // tensor core works on S_{j+1} while the softmax warps chew on S_j
-      mbar_wait_bounded(&p_full[s], (j >> 1) & 1);
+      mbar_wait_bounded(&p_full[sb], (j >> 1) & 1);
+      mbar_wait_bounded(&v_full[s], (j / NST) & 1);
       tc_fence_after();
-      const uint32_t aV = smem_u32(sKV + s * (K_BYTES + V_BYTES) + K_BYTES);
+      const uint32_t aV = smem_u32(sV0 + s * V_BYTES);
 #pragma unroll
       for (int k = 0; k < BKV / 16; ++k) {
         // V_j as B operand, MN-major: 64-wide hd blocks BKV*128 B apart (LBO), 8-key groups 1024 B apart (SBO), 16 keys = 2048 B per MMA
         const uint64_t db = smem_desc(aV + k * 2048, BKV * 128, 1024);
-        umma_f16_ts(tO, tS0 + s * BKV + k * 8, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);     // P: 16 bf16 = 8 TMEM columns per MMA
+        umma_f16_ts(tO, tS0 + sb * BKV + k * 8, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);     // P: 16 bf16 = 8 TMEM columns per MMA
       }
-      umma_commit(&kv_empty[s]);
+      umma_commit(&v_empty[s]);
       umma_commit(&pv_done);
     }
   } else if (warp >= 2) {
@@ -281,7 +297,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 
 template <int HD>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
-  constexpr int SMEM = BQ * HD * 2 + 2 * (2 * BKV * HD * 2) + 1024;
+  constexpr int SMEM = BQ * HD * 2 + ((HD == 64) ? 4 : 2) * (2 * BKV * HD * 2) + 1024;
   static bool attr = false;
   if (!attr) {
     LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));

@@ -23,8 +23,8 @@ def _need_cuda(*ts):
 
 
 # ---------------------------------------------------------------------------------------------------
-# GEMM plumbing.  Plain library GEMMs (cuBLAS through torch) for the dense contractions; every fused /
-# irregular op around them is one of our kernels.
+# GEMM plumbing.  Every dense contraction of the path (forward, dgrad, wgrad, grouped expert forms) runs on the hand-written tcgen05 /
+# TMA GEMM of csrc/gemm.cu through lmod_gemm_bf16 / lmod_grouped_gemm_bf16; no library GEMM is called.
 # ---------------------------------------------------------------------------------------------------
 def _rows(t):
     t2 = t.reshape(-1, t.shape[-1])
@@ -717,7 +717,8 @@ def logp_gather(logits, labels, average=False):
     tok = torch.empty(B * T, dtype=torch.float32, device=dev)
     lse = torch.empty(B * T, dtype=torch.float32, device=dev)
     seq = torch.empty(B, dtype=torch.float32, device=dev)
-    call("lmod_logp_gather_fwd", ptr(logits), logits.stride(1), ptr(labels), B, T, V, ptr(tok), ptr(lse), ptr(seq), 1 if average else 0)
+    with _Timed("logp_fwd"):
+        call("lmod_logp_gather_fwd", ptr(logits), logits.stride(1), ptr(labels), B, T, V, ptr(tok), ptr(lse), ptr(seq), 1 if average else 0)
     return seq, tok, lse
 
 
@@ -739,7 +740,8 @@ class LogpHeadFn(Function):
         logits, w_head, labels, lse, hidden = ctx.saved_tensors
         B, T, V = logits.shape
         g = _c(g.to(torch.float32))
-        call("lmod_logp_gather_bwd", ptr(logits), logits.stride(1), ptr(labels), B, T, V, ptr(lse), ptr(g), 0, ptr(logits), logits.stride(1))
+        with _Timed("logp_bwd"):
+            call("lmod_logp_gather_bwd", ptr(logits), logits.stride(1), ptr(labels), B, T, V, ptr(lse), ptr(g), 0, ptr(logits), logits.stride(1))
         d2 = logits.view(B * T, V)
         dh = mm_nn(d2, w_head).view(hidden.shape)
         if ctx.head_grad is not None:

@@ -70,6 +70,12 @@ def create_model_tokenizer(model_args, data_args, training_args, name_or_path, m
     else:
         raise FileNotFoundError("%s: no local checkpoint (no network); set LLAVAMOD_ALLOW_RANDOM_INIT=1 for synthetic weights" % name_or_path)
     model.config.use_cache = False
+    if getattr(model_args, "freeze_backbone", False):                 # align_train.py:255-256
+        model.model.requires_grad_(False)
+    if getattr(model_args, "tune_llm_ffn_only", False):               # align_train.py:258-266
+        for name, param in model.named_parameters():
+            if "image_tower" not in name:
+                param.requires_grad = any(n in name for n in ("mlp.gate_proj", "mlp.up_proj", "mlp.down_proj"))
     if sparse:
         model.initialize_moe_modules(model_args)
     if model_args.image_tower is not None:
@@ -78,6 +84,16 @@ def create_model_tokenizer(model_args, data_args, training_args, name_or_path, m
         model.get_model().initialize_vision_modules(margs)
         model.config.image_aspect_ratio = data_args.image_aspect_ratio
         model.config.tokenizer_padding_side = "right"
+        model.config.tune_mm_mlp_adapter = training_args.tune_mm_mlp_adapter = model_args.tune_mm_mlp_adapter      # align_train.py:473-477
+        if model_args.tune_mm_mlp_adapter:
+            model.requires_grad_(False)
+            for p in model.get_model().mm_projector.parameters():
+                p.requires_grad = True
+        model.config.freeze_mm_mlp_adapter = training_args.freeze_mm_mlp_adapter                                      # align_train.py:479-482
+        if training_args.freeze_mm_mlp_adapter:
+            for p in model.get_model().mm_projector.parameters():
+                p.requires_grad = False
+        model.config.mm_projector_lr = training_args.mm_projector_lr
     return model, None
 
 
@@ -130,6 +146,8 @@ def make_supervised_data_module(data_args, training_args, model, tokenizer=None)
             raise ValueError("--data_path %s needs a tokenizer next to the policy checkpoint" % path)
         data_args.image_processor = model.get_image_tower().image_processor
         data_args.is_multimodal = True
+        if not hasattr(data_args, "mm_use_im_start_end"):           # set from --mm_use_im_start_end by the entry points (align_train.py:487)
+            data_args.mm_use_im_start_end = False
         return make_json_module(tokenizer, data_args)
     n = int(path.split(":")[1]) if ":" in path else 1024
     tower = model.get_image_tower()
@@ -155,6 +173,7 @@ def train(argv=None):
                                           align_args.ref_model_type, align_args.ref_pretrain_mm_mlp_adapter, device)
     training_args.moe_enable = model_args.moe_enable
     training_args.tune_mm_mlp_adapter = model_args.tune_mm_mlp_adapter
+    model.config.mm_use_im_start_end = data_args.mm_use_im_start_end = model_args.mm_use_im_start_end      # align_train.py:487
     path = (data_args.data_path or ["synthetic"])[0]
     tokenizer = None
     if not str(path).startswith("synthetic"):

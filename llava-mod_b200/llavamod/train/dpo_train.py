@@ -61,6 +61,7 @@ def train(argv=None):
         model.config.pad_token_id = tokenizer.pad_token_id
         data_args.image_processor = tower.image_processor
         data_args.is_multimodal = True
+        data_args.mm_use_im_start_end = model.config.mm_use_im_start_end = bool(getattr(model_args, "mm_use_im_start_end", False))   # dpo_train.py: same line as align_train.py:487
         data_module = make_dpo_data_module(tokenizer, data_args)
     else:
         tokenizer = None

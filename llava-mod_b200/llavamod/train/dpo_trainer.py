@@ -46,9 +46,12 @@ class DPOTrainer(BaseTrainer):
         for p in self.ref_model.module.parameters():
             p.requires_grad = False
         self.share_tower = same_frozen_tower(self.model, self.ref_model.module)
+        import os
+        self.overlap_teacher = bool(int(os.environ.get("LLAVAMOD_OVERLAP_TEACHER", "1"))) and next(model.parameters()).is_cuda
+        self._teacher_stream = torch.cuda.Stream() if self.overlap_teacher else None
 
-    def _seq_logp(self, model, fwd, tower_feats, noise=None, grad=True):
-        r = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=noise)
+    def _seq_logp(self, model, fwd, tower_feats, noise=None, grad=True, plan=None):
+        r = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=noise, plan=plan)
         if r["hidden"].shape[:2] != r["labels"].shape:
             raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
         if grad:
@@ -107,12 +110,28 @@ class DPOTrainer(BaseTrainer):
                 tower_feats = model.get_image_tower()(images.to(model.dtype))                 # once instead of 4x (dpo_trainer.py:595-607)
         ch = dict(input_ids=inputs["chosen_input_ids"], labels=inputs["chosen_labels"], attention_mask=inputs["chosen_attention_mask"], images=images)
         rj = dict(input_ids=inputs["rejected_input_ids"], labels=inputs["rejected_labels"], attention_mask=inputs["rejected_attention_mask"], images=images)
-        with torch.no_grad():
-            reference_chosen_logps, _ = self._seq_logp(ref, ch, tower_feats, grad=False)
-            reference_rejected_logps, _ = self._seq_logp(ref, rj, tower_feats, grad=False)
+        # one host splice plan per side, shared by the reference and the policy forward when their towers emit the same patch count
+        plan_c, plan_r = inputs.get("splice_plan_chosen"), inputs.get("splice_plan_rejected")
+        if plan_c is None and images is not None and model.get_image_tower() is not None and \
+                model.get_image_tower().num_patches == ref.get_image_tower().num_patches:
+            plan_c = model.make_splice_plan(ch["input_ids"], ch["attention_mask"], ch["labels"])
+            plan_r = model.make_splice_plan(rj["input_ids"], rj["attention_mask"], rj["labels"])
+        # the two frozen reference forwards are independent of the policy until dpo_loss: they run on a side stream so the 0.5B policy's
+        # small kernels fill the gaps of the 7B reference's machine-filling GEMMs (a fork/join inside the CUDA graph), as in AlignTrainer
+        main = torch.cuda.current_stream()
+        side = self._teacher_stream if self.overlap_teacher else None
+        if side is not None:
+            side.wait_stream(main)
+        with torch.no_grad(), torch.cuda.stream(side if side is not None else main):
+            reference_chosen_logps, _ = self._seq_logp(ref, ch, tower_feats, grad=False, plan=plan_c)
+            reference_rejected_logps, _ = self._seq_logp(ref, rj, tower_feats, grad=False, plan=plan_r)
         noise = inputs.get("moe_noise") or (None, None)
-        policy_chosen_logps, rc = self._seq_logp(model, ch, tower_feats, noise[0])
-        policy_rejected_logps, rr = self._seq_logp(model, rj, tower_feats, noise[1])
+        policy_chosen_logps, rc = self._seq_logp(model, ch, tower_feats, noise[0], plan=plan_c)
+        policy_rejected_logps, rr = self._seq_logp(model, rj, tower_feats, noise[1], plan=plan_r)
+        if side is not None:
+            main.wait_stream(side)
+            reference_chosen_logps.record_stream(main)
+            reference_rejected_logps.record_stream(main)
         reward_losses, chosen_rewards, rejected_rewards = self.dpo_loss(policy_chosen_logps, policy_rejected_logps,
                                                                         reference_chosen_logps, reference_rejected_logps)
         enabled = getattr(self.args, "moe_enable", False) and self.moe_loss_enable and getattr(model, "is_moe", False)
@@ -141,8 +160,49 @@ class DPOTrainer(BaseTrainer):
         return losses.mean()
 
     def store_metrics(self, metrics: Dict[str, float], train_eval: Literal["train", "eval"] = "train") -> None:
+        if self._suppress_store:          # graph capture: the static output tensors are cloned after every replay instead
+            return
         for key, value in metrics.items():
             self._stored_metrics[train_eval][key].append(value)
+
+    # ---- CUDA-graph plumbing (see BaseTrainer._graphed_micro_batch): the four forwards + two backwards of a pair are captured once per
+    # input signature; static inputs = the image tensor and the two splice plans ------------------------------------------------------
+    def _graph_signature(self, inputs, next_inputs=None):
+        images = inputs.get("images")
+        if images is None or inputs.get("moe_noise") is not None or not self.share_tower:
+            return None
+        for side in ("chosen", "rejected"):
+            if inputs.get("splice_plan_" + side) is None:
+                inputs["splice_plan_" + side] = self.model.make_splice_plan(inputs[side + "_input_ids"], inputs.get(side + "_attention_mask"),
+                                                                            inputs[side + "_labels"])
+        pc, pr = inputs["splice_plan_chosen"], inputs["splice_plan_rejected"]
+        if not (pc["all_true"] and pr["all_true"]):
+            return None                   # padded pairs run eagerly
+        n_img = len(images) if not torch.is_tensor(images) else images.shape[0]
+        ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
+        return ("dpo", tuple(pc["src"].shape), tuple(pr["src"].shape), n_img, ish, pc["has_mask"], pr["has_mask"], self.loss_type)
+
+    def _graph_static_inputs(self, inputs, static):
+        images = inputs["images"]
+        if static is None:
+            dev = self.model.device
+            n = len(images) if not torch.is_tensor(images) else images.shape[0]
+            ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
+            static = {k: inputs[k] for k in ("chosen_input_ids", "chosen_labels", "chosen_attention_mask", "rejected_input_ids",
+                                             "rejected_labels", "rejected_attention_mask")}
+            static["images"] = torch.empty((n,) + ish, dtype=self.model.dtype, device=dev)
+            for side in ("chosen", "rejected"):
+                static["splice_plan_" + side] = {k: (torch.empty_like(v) if torch.is_tensor(v) else v) for k, v in inputs["splice_plan_" + side].items()}
+        if torch.is_tensor(images):
+            static["images"].copy_(images, non_blocking=True)
+        else:
+            for i, im in enumerate(images):
+                static["images"][i].copy_(im, non_blocking=True)
+        for side in ("chosen", "rejected"):
+            for k, v in inputs["splice_plan_" + side].items():
+                if torch.is_tensor(v):
+                    static["splice_plan_" + side][k].copy_(v, non_blocking=True)
+        return static
 
     def log(self, logs: Dict[str, float]) -> None:
         train_eval = "train" if "loss" in logs else "eval"

@@ -202,10 +202,14 @@ class TrainState:
         return float(torch.sqrt(self.gnorm_sq)[0]) * grad_scale
 
 
-def cosine_lr(step, total, base_lr, warmup_ratio=0.03):
-    """transformers.get_cosine_schedule_with_warmup with warmup = ceil(ratio*total) (HF TrainingArguments.get_warmup_steps);
-    ``step`` = number of completed optimizer steps."""
-    warm = math.ceil(warmup_ratio * total)
+def warmup_steps_of(total, warmup_ratio=0.0, warmup_steps=0):
+    """HF TrainingArguments.get_warmup_steps: --warmup_steps wins when > 0, else ceil(ratio * total)."""
+    return int(warmup_steps) if warmup_steps and warmup_steps > 0 else math.ceil(warmup_ratio * total)
+
+
+def cosine_lr(step, total, base_lr, warmup_ratio=0.03, warmup_steps=0):
+    """transformers.get_cosine_schedule_with_warmup with HF's warm-up step count; ``step`` = number of completed optimizer steps."""
+    warm = warmup_steps_of(total, warmup_ratio, warmup_steps)
     if step < warm:
         return base_lr * step / max(1, warm)
     prog = (step - warm) / max(1, total - warm)

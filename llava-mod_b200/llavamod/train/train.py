@@ -51,6 +51,7 @@ def train(argv=None):
     model, _ = create_model_tokenizer(model_args, data_args, training_args, model_args.model_name_or_path,
                                       "sparse" if model_args.moe_enable else "dense", model_args.pretrain_mm_mlp_adapter, device)
     training_args.moe_enable = model_args.moe_enable
+    model.config.mm_use_im_start_end = data_args.mm_use_im_start_end = model_args.mm_use_im_start_end      # train.py (reference): same assignment
     select_trainable(model, model_args, training_args)
     path = (data_args.data_path or ["synthetic"])[0]
     tokenizer = None

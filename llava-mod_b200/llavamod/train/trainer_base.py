@@ -15,7 +15,7 @@ from collections import defaultdict
 import torch
 import torch.distributed as dist
 
-from .engine import TrainState, cosine_lr
+from .engine import TrainState, cosine_lr, warmup_steps_of
 
 
 def _with_lookahead(iterable):
@@ -82,11 +82,11 @@ class BaseTrainer:
         a = self.args
         if self._total_steps is None or a.lr_scheduler_type == "constant":
             return a.learning_rate
+        wsteps = getattr(a, "warmup_steps", 0) or 0
         if a.lr_scheduler_type == "cosine":
-            return cosine_lr(self.state.global_step, self._total_steps, a.learning_rate, a.warmup_ratio)
+            return cosine_lr(self.state.global_step, self._total_steps, a.learning_rate, a.warmup_ratio, wsteps)
         if a.lr_scheduler_type == "linear":
-            import math
-            warm = math.ceil(a.warmup_ratio * self._total_steps)
+            warm = warmup_steps_of(self._total_steps, a.warmup_ratio, wsteps)
             s = self.state.global_step
             if s < warm:
                 return a.learning_rate * s / max(1, warm)

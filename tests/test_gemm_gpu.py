@@ -71,14 +71,14 @@ def test_gemm_fused_swiglu_epilogue():
     assert fused is not None
     two_step = Kk.silu_mul(Kk.gemm(x, w))
     assert torch.equal(fused, two_step)
-    # the interleaved copy follows the weights: an in-place update through torch (load_state_dict path) rebuilds it
-    with torch.no_grad():
-        mlp.gate_proj.weight.mul_(0.5)
-    assert torch.equal(Kk.swiglu_mlp_in(x, mlp), Kk.silu_mul(Kk.gemm(x, w)))
     ref = torch.nn.functional.silu(x.float() @ w[:I].float().t()) * (x.float() @ w[I:].float().t())
     # vs the un-rounded fp32 formula: gate, up and silu(gate) are each rounded to bf16 on the way (as in the reference's bf16 modules)
     err = (fused.float() - ref).abs()
     assert bool((err <= 2.0 ** -6 * ref.abs() + 0.05).all()), err.max().item()
+    # the interleaved copy follows the weights: an in-place update through torch (load_state_dict path) rebuilds it
+    with torch.no_grad():
+        mlp.gate_proj.weight.mul_(0.5)
+    assert torch.equal(Kk.swiglu_mlp_in(x, mlp), Kk.silu_mul(Kk.gemm(x, w)))
 
 
 def test_gemm_bias_beta_and_f32_accumulate():
