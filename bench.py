@@ -635,6 +635,7 @@ def secondary(args, job, teacher, student, rank, world, dev, barrier, reduce_max
     try:
         for t in job.trainers.values():
             t._graphs.clear()
+            t._statics.clear()
         torch.cuda.empty_cache()
         name5 = "mimic+pref-1.8B-8E-from-7B-seq4096"
         wl5 = WORKLOADS[name5]

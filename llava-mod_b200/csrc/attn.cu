@@ -7,8 +7,8 @@
 // One CTA = one (batch, head, 128-query block); two CTAs are co-resident per SM so one CTA's softmax overlaps the other's MMAs.
 // Padded batches (right or left padding, per-row key range [kv_lo, kv_hi)) run on the same kernel: the CTA walks only the key blocks
 // its rows can see and masks per element; rows with no visible key are un-masked as in the reference's 4-D mask.
-//   warp 0 lane 0 / lane 1 : TMA producers -- Q tile once and the K ring / the V ring (blocks of 64 keys, 128B swizzle; separate rings so K
-//                                   runs NST blocks ahead of its use)
+//   warp 0 lane 0 : TMA producer -- Q tile once, then the K ring and the V ring (blocks of 64 keys, 128B swizzle; separate rings and
+//                                   barriers, so K runs NST blocks ahead of its use)
 //   warp 1 lane 0 : MMA issuer   -- S_j = Q K_j^T (SS, M=128 N=64 K=16 x hd/16) into one of two S buffers in TMEM;
 //                                   O += P_j V_j (TS: A = P_j read from TMEM, B = V_j MN-major from smem, N = hd)
 //   warps 2..9    : softmax      -- two threads per query row (TMEM lane = row; warps 2-5 take key columns 0-31 of each block, warps 6-9
@@ -121,27 +121,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   const uint32_t tS0 = tmem, tO = tmem + 2 * BKV;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer: Q once, then the K ring =====================
+    // ===================== TMA producer: Q once, then the K ring and the V ring, whichever has a free slot (K first) =====================
     mbar_expect_tx(&q_full, Q_BYTES);
 #pragma unroll
     for (int i = 0; i < KSUB; ++i) tma_load_2d(sQ + i * (BQ * 128), &tma_q, col_q + 64 * i, row_base + q0, &q_full);
-    for (int j = 0; j < nblk; ++j) {
-      const int s = j % NST;
-      mbar_wait_bounded(&k_empty[s], ((j / NST) & 1) ^ 1);
-      uint8_t* sK = sK0 + s * K_BYTES;
-      mbar_expect_tx(&k_full[s], K_BYTES);
+    int jk = 0, jv = 0;
+    uint32_t spins = 0;
+    while (jk < nblk || jv < nblk) {
+      bool progressed = false;
+      if (jk < nblk) {
+        const int s = jk % NST;
+        if (jk < NST || mbar_try_wait(&k_empty[s], ((jk / NST) & 1) ^ 1)) {
+          uint8_t* sK = sK0 + s * K_BYTES;
+          mbar_expect_tx(&k_full[s], K_BYTES);
 #pragma unroll
-      for (int i = 0; i < KSUB; ++i) tma_load_2d(sK + i * (BKV * 128), &tma_kv, col_k + 64 * i, row_base + (jb + j) * BKV, &k_full[s]);
-    }
-  } else if (warp == 0 && lane == 1) {
-    // ===================== TMA producer: the V ring =====================
-    for (int j = 0; j < nblk; ++j) {
-      const int s = j % NST;
-      mbar_wait_bounded(&v_empty[s], ((j / NST) & 1) ^ 1);
-      uint8_t* sV = sV0 + s * V_BYTES;
-      mbar_expect_tx(&v_full[s], V_BYTES);
+          for (int i = 0; i < KSUB; ++i) tma_load_2d(sK + i * (BKV * 128), &tma_kv, col_k + 64 * i, row_base + (jb + jk) * BKV, &k_full[s]);
+          ++jk; progressed = true;
+        }
+      }
+      if (jv < nblk && (jv < jk || jk == nblk)) {            // V never runs ahead of K: the K of a block is needed first
+        const int s = jv % NST;
+        if (jv < NST || mbar_try_wait(&v_empty[s], ((jv / NST) & 1) ^ 1)) {
+          uint8_t* sV = sV0 + s * V_BYTES;
+          mbar_expect_tx(&v_full[s], V_BYTES);
 #pragma unroll
-      for (int i = 0; i < KSUB; ++i) tma_load_2d(sV + i * (BKV * 128), &tma_kv, col_v + 64 * i, row_base + (jb + j) * BKV, &v_full[s]);
+          for (int i = 0; i < KSUB; ++i) tma_load_2d(sV + i * (BKV * 128), &tma_kv, col_v + 64 * i, row_base + (jb + jv) * BKV, &v_full[s]);
+          ++jv; progressed = true;
+        }
+      }
+      if (progressed) spins = 0;
+      else if (++spins > (1u << 26)) { printf("lmod attn_fwd_kernel: producer timeout (block %d)\n", blockIdx.x); __trap(); }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================

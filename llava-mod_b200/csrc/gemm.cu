@@ -39,7 +39,26 @@ struct GemmParams {
   int bn;                          // tile width (256 or 128)
   int beta;                        // 1: D = bf16(D + acc)
   int splits;                      // split-K factor (>1: fp32 atomic accumulation into D32)
-  int swiglu;                      // CTA-pair kernel only: tile = [128 gate | 128 up] columns -> D[:, N/2] = bf16(bf16(silu(g)) * u)
+  // fused SwiGLU forward (Qwen2MLP act_fn(gate_proj(x)) * up_proj(x), modeling_qwen2.py:199-200): B is the fused gate|up weight [2I, K]
+  // as stored (gate rows, then up rows); N = I; an output tile = 128 act columns whose accumulator holds [128 gate | 128 up] columns (the
+  // two halves of the B stage are loaded from rows n0 and I + n0).  D[:, I] = bf16(bf16(silu(g)) * u); H1 (optional) keeps the bf16
+  // pre-activations [M, 2I] for the backward.
+  int swiglu;
+  int swiglu_I;
+  __nv_bfloat16* H1;
+  int64_t ld_h1;
+  // fused SwiGLU backward in the epilogue of the down_proj dgrad (dact = dY W_dn, N = I): reads the saved pre-activations GU [M, 2I],
+  // writes d(gate) | d(up) into D [M, 2I] (columns col and I + col) -- the [M, I] dact tensor never exists
+  int silu_bwd;
+  const __nv_bfloat16* GU;
+  int64_t ld_gu;
+  // fused rotary embedding in the epilogue of the q|k|v projection (apply_rotary_pos_emb, modeling_qwen2.py:159-184): columns below
+  // rope_cols (the q and k heads) are rotated per head of rope_hd columns with cos / sin [max_pos, rope_hd] rows picked by rope_pos[row];
+  // the v columns pass through.  Same bf16 roundings as GEMM(+bias) followed by lmod_rope (bit-identical).
+  const __nv_bfloat16* rope_cos;
+  const __nv_bfloat16* rope_sin;
+  const int64_t* rope_pos;
+  int rope_hd, rope_cols;
   int dbg_nostore;                 // timing experiments only (LMOD_GEMM_NOSTORE=1): epilogue drains TMEM but does not write D
   // grouped (experts): row ranges from `offsets` (device), B / D32 advance per group
   const int32_t* offsets;          // [groups+1] or null
@@ -77,6 +96,78 @@ __device__ __forceinline__ uint32_t instr_desc() {
 }
 
 struct Tile { int m0, n0, kb0, kb1, group, m_end; };
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+// rotate 8 (x1, x2) pairs of one head: x = bf16(acc + bias); o1 = bf16(bf16(x1 c) + bf16(-x2 s)), o2 = bf16(bf16(x2 c) + bf16(x1 s))
+// (the expression of rope_vec_kernel).  a1 / a2: fp32 accumulators of the first-half / second-half columns, b1 / b2: their bias (or null).
+__device__ __forceinline__ void rope_store8(const uint32_t* a1, const uint32_t* a2, const __nv_bfloat16* b1, const __nv_bfloat16* b2, const __nv_bfloat16* cs,
+                                            const __nv_bfloat16* sn, __nv_bfloat16* d1, __nv_bfloat16* d2) {
+  float x1[8], x2[8], c[8], s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { x1[j] = __uint_as_float(a1[j]); x2[j] = __uint_as_float(a2[j]); }
+  if (b1) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(b1)), w = __ldg(reinterpret_cast<const uint4*>(b2));
+    x1[0] += bf16lo(u.x); x1[1] += bf16hi(u.x); x1[2] += bf16lo(u.y); x1[3] += bf16hi(u.y);
+    x1[4] += bf16lo(u.z); x1[5] += bf16hi(u.z); x1[6] += bf16lo(u.w); x1[7] += bf16hi(u.w);
+    x2[0] += bf16lo(w.x); x2[1] += bf16hi(w.x); x2[2] += bf16lo(w.y); x2[3] += bf16hi(w.y);
+    x2[4] += bf16lo(w.z); x2[5] += bf16hi(w.z); x2[6] += bf16lo(w.w); x2[7] += bf16hi(w.w);
+  }
+  {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(cs)), w = __ldg(reinterpret_cast<const uint4*>(sn));
+    c[0] = bf16lo(u.x); c[1] = bf16hi(u.x); c[2] = bf16lo(u.y); c[3] = bf16hi(u.y); c[4] = bf16lo(u.z); c[5] = bf16hi(u.z); c[6] = bf16lo(u.w); c[7] = bf16hi(u.w);
+    s[0] = bf16lo(w.x); s[1] = bf16hi(w.x); s[2] = bf16lo(w.y); s[3] = bf16hi(w.y); s[4] = bf16lo(w.z); s[5] = bf16hi(w.z); s[6] = bf16lo(w.w); s[7] = bf16hi(w.w);
+  }
+  float o1[8], o2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float y1 = bf16_round(x1[j]), y2 = bf16_round(x2[j]);
+    o1[j] = bf16_round(y1 * c[j]) + bf16_round(-y2 * s[j]);
+    o2[j] = bf16_round(y2 * c[j]) + bf16_round(y1 * s[j]);
+  }
+  uint4 w;
+  w.x = pack_bf16x2(o1[0], o1[1]); w.y = pack_bf16x2(o1[2], o1[3]); w.z = pack_bf16x2(o1[4], o1[5]); w.w = pack_bf16x2(o1[6], o1[7]);
+  *reinterpret_cast<uint4*>(d1) = w;
+  w.x = pack_bf16x2(o2[0], o2[1]); w.y = pack_bf16x2(o2[2], o2[3]); w.z = pack_bf16x2(o2[4], o2[5]); w.w = pack_bf16x2(o2[6], o2[7]);
+  *reinterpret_cast<uint4*>(d2) = w;
+}
+// act = bf16(bf16(silu(g)) * u) on bf16-rounded GEMM outputs: the expression of silu_mul_fwd_kernel (bit-identical to GEMM + that kernel)
+__device__ __forceinline__ void swiglu_store8(const uint32_t* g, const uint32_t* u, __nv_bfloat16* act, __nv_bfloat16* h1g, __nv_bfloat16* h1u) {
+  float gb[8], ub[8], f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gb[j] = bf16_round(__uint_as_float(g[j])); ub[j] = bf16_round(__uint_as_float(u[j]));
+    f[j] = bf16_round(gb[j] * sigmoid_f(gb[j])) * ub[j];
+  }
+  uint4 w;
+  w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(act) = w;
+  if (h1g) {
+    w.x = pack_bf16x2(gb[0], gb[1]); w.y = pack_bf16x2(gb[2], gb[3]); w.z = pack_bf16x2(gb[4], gb[5]); w.w = pack_bf16x2(gb[6], gb[7]);
+    *reinterpret_cast<uint4*>(h1g) = w;
+    w.x = pack_bf16x2(ub[0], ub[1]); w.y = pack_bf16x2(ub[2], ub[3]); w.z = pack_bf16x2(ub[4], ub[5]); w.w = pack_bf16x2(ub[6], ub[7]);
+    *reinterpret_cast<uint4*>(h1u) = w;
+  }
+}
+// d(gate), d(up) from dact (the fp32 accumulator rounded to bf16, as the unfused path materialises it) and the saved pre-activations:
+// the expression of silu_mul_bwd_kernel
+__device__ __forceinline__ void silu_bwd_store8(const float* dacc, const __nv_bfloat16* gp, const __nv_bfloat16* up, __nv_bfloat16* dgp, __nv_bfloat16* dup) {
+  const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gp)), uv = __ldg(reinterpret_cast<const uint4*>(up));
+  const float g[8] = {bf16lo(gv.x), bf16hi(gv.x), bf16lo(gv.y), bf16hi(gv.y), bf16lo(gv.z), bf16hi(gv.z), bf16lo(gv.w), bf16hi(gv.w)};
+  const float u[8] = {bf16lo(uv.x), bf16hi(uv.x), bf16lo(uv.y), bf16hi(uv.y), bf16lo(uv.z), bf16hi(uv.z), bf16lo(uv.w), bf16hi(uv.w)};
+  float dg[8], du[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float d = bf16_round(dacc[j]);
+    const float sg = sigmoid_f(g[j]);
+    du[j] = d * g[j] * sg;
+    dg[j] = d * u[j] * sg * (1.f + g[j] * (1.f - sg));
+  }
+  uint4 w;
+  w.x = pack_bf16x2(dg[0], dg[1]); w.y = pack_bf16x2(dg[2], dg[3]); w.z = pack_bf16x2(dg[4], dg[5]); w.w = pack_bf16x2(dg[6], dg[7]);
+  *reinterpret_cast<uint4*>(dgp) = w;
+  w.x = pack_bf16x2(du[0], du[1]); w.y = pack_bf16x2(du[2], du[3]); w.z = pack_bf16x2(du[4], du[5]); w.w = pack_bf16x2(du[6], du[7]);
+  *reinterpret_cast<uint4*>(dup) = w;
+}
 
 // tile index -> coordinates.  Dense: M fastest (consecutive CTAs share the B tile in L2).  Grouped forward/dgrad: per-group row
 // ranges [offsets[g], offsets[g+1]) (128-row aligned by the router), B rows offset by g*b_group_rows.  Grouped wgrad: each group owns
@@ -160,7 +251,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tma_a, t.m0 + 64 * j, kb * BK, &full_bar[stage]);   // box (64 mn, 64 k)
         }
-        if (!B_MN) {
+        if (!B_MN && p.swiglu) {                                                         // box (64 k, 128 rows): gate rows, then the matching up rows
+          tma_load_2d(sb, &tma_b, kb * BK, b_row0 + t.n0, &full_bar[stage]);
+          tma_load_2d(sb + 128 * 128, &tma_b, kb * BK, b_row0 + p.swiglu_I + t.n0, &full_bar[stage]);
+        } else if (!B_MN) {
           tma_load_2d(sb, &tma_b, kb * BK, b_row0 + t.n0, &full_bar[stage]);             // box (64 k, 256 rows)
         } else {
 #pragma unroll
@@ -208,11 +302,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const bool empty_k = t.kb1 <= t.kb0;                 // grouped wgrad of an expert with no rows: contributes zero
       __nv_bfloat16* drow = p.D ? p.D + (p.wgrad_grouped ? t.group * p.d_group_stride : 0) + (int64_t)row * p.ldd : nullptr;
       float* d32row = p.D32 ? p.D32 + (p.wgrad_grouped ? t.group * p.d_group_stride : 0) + (int64_t)row * p.ldd : nullptr;
+      if (BN == 256 && p.swiglu) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), g);
+          tmem_ld32(tmem_base + acc * BN + 128 + c * 32 + ((uint32_t)(q * 32) << 16), u);
+          const int col0 = t.n0 + c * 32;
+          if (!row_ok || col0 >= p.N) continue;
+          __nv_bfloat16* h1row = p.H1 ? p.H1 + (int64_t)row * p.ld_h1 : nullptr;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int col = col0 + v * 8;
+            swiglu_store8(g + v * 8, u + v * 8, drow + col, h1row ? h1row + col : nullptr, h1row ? h1row + p.swiglu_I + col : nullptr);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
         const int col0 = t.n0 + c * 32;
+        if (p.rope_cos && col0 < p.rope_cols) {
+          // q / k head columns: the chunk of the first half of a head is processed together with its partner half a head further on
+          const int hoff = col0 % p.rope_hd, half = p.rope_hd >> 1;
+          if (hoff >= half) continue;                                   // done with its partner
+          uint32_t r2[32];
+          tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+          tmem_ld32(tmem_base + acc * BN + c * 32 + half + ((uint32_t)(q * 32) << 16), r2);
+          if (!row_ok) continue;
+          const int64_t pp = __ldg(p.rope_pos + row);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int col = col0 + v * 8, d = hoff + v * 8;
+            rope_store8(r + v * 8, r2 + v * 8, p.bias ? p.bias + col : nullptr, p.bias ? p.bias + col + half : nullptr,
+                        p.rope_cos + pp * p.rope_hd + d, p.rope_sin + pp * p.rope_hd + d, drow + col, drow + col + half);
+          }
+          continue;
+        }
+        tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
         if (!row_ok || col0 >= p.N || p.dbg_nostore) continue;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -226,7 +357,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
             f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
           }
-          if (d32row && p.splits > 1) {
+          if (p.silu_bwd) {
+            const __nv_bfloat16* gurow = p.GU + (int64_t)row * p.ld_gu;
+            silu_bwd_store8(f, gurow + col, gurow + p.N + col, drow + col, drow + p.N + col);
+          } else if (d32row && p.splits > 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) atomicAdd(d32row + col + j, f[j]);
           } else if (d32row) {
@@ -299,7 +433,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-  const int num_m = (p.M + 255) / 256, num_n = (p.N + 255) / 256, num_k = (p.K + BK - 1) / BK;
+  // SwiGLU forward: N = I and a pair's tile is 256 rows x 128 act columns (accumulator: 128 gate | 128 up columns, one half per CTA's B)
+  const int num_m = (p.M + 255) / 256, num_n = p.swiglu ? (p.N + 127) / 128 : (p.N + 255) / 256, num_k = (p.K + BK - 1) / BK;
   const int ntiles = num_m * num_n;
 
   if (threadIdx.x == 0) {
@@ -323,7 +458,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     // ===================== TMA producer (both CTAs: own half of A rows and of B rows) =====================
     uint32_t stage = 0, phase = 0;
     for (int t = cluster; t < ntiles; t += nclusters) {
-      const int m0 = (t % num_m) * 256 + 128 * (int)rank, n0 = (t / num_m) * 256 + 128 * (int)rank;
+      const int m0 = (t % num_m) * 256 + 128 * (int)rank;
+      const int n0 = p.swiglu ? (t / num_m) * 128 + (int)rank * p.swiglu_I           // rank 0 stages the gate rows, rank 1 the matching up rows
+                              : (t / num_m) * 256 + 128 * (int)rank;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE2_BYTES;
@@ -383,26 +520,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       __nv_bfloat16* drow = p.D ? p.D + (int64_t)row * p.ldd : nullptr;
       float* d32row = p.D32 ? p.D32 + (int64_t)row * p.ldd : nullptr;
       if (p.swiglu) {
-        // fused SwiGLU epilogue (Qwen2MLP act_fn(gate_proj(x)) * up_proj(x), modeling_qwen2.py:199-200): the weight rows of this
-        // 256-wide tile are [128 gate rows | 128 matching up rows], so gate and up of the same output column sit in this thread's lane
+        // fused SwiGLU epilogue: accumulator columns [0,128) = gate, [128,256) = up of the same 128 act columns
+        const int c00 = (t / num_m) * 128;
+        __nv_bfloat16* h1row = p.H1 ? p.H1 + (int64_t)row * p.ld_h1 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t g[32], u[32];
           tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), g);
           tmem_ld32(tmem_base + acc * 256 + 128 + c * 32 + ((uint32_t)(q * 32) << 16), u);
-          const int col0 = (n00 >> 1) + c * 32;
-          if (!row_ok || col0 >= (p.N >> 1)) continue;
+          const int col0 = c00 + c * 32;
+          if (!row_ok || col0 >= p.N) continue;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float gb = bf16_round(__uint_as_float(g[v * 8 + j])), ub = bf16_round(__uint_as_float(u[v * 8 + j]));   // reference rounds both GEMM outputs to bf16
-              f[j] = bf16_round(gb * (1.f / (1.f + __expf(-gb)))) * ub;      // same expression as silu_mul_fwd_kernel -> bit-identical
-            }
-            uint4 w;
-            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(drow + col0 + v * 8) = w;
+            const int col = col0 + v * 8;
+            swiglu_store8(g + v * 8, u + v * 8, drow + col, h1row ? h1row + col : nullptr, h1row ? h1row + p.swiglu_I + col : nullptr);
           }
         }
         tc_fence_before();
@@ -413,8 +544,24 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
         const int col0 = n00 + c * 32;
+        if (p.rope_cos && col0 < p.rope_cols) {
+          const int hoff = col0 % p.rope_hd, half = p.rope_hd >> 1;
+          if (hoff >= half) continue;
+          uint32_t r2[32];
+          tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
+          tmem_ld32(tmem_base + acc * 256 + c * 32 + half + ((uint32_t)(q * 32) << 16), r2);
+          if (!row_ok) continue;
+          const int64_t pp = __ldg(p.rope_pos + row);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int col = col0 + v * 8, d = hoff + v * 8;
+            rope_store8(r + v * 8, r2 + v * 8, p.bias ? p.bias + col : nullptr, p.bias ? p.bias + col + half : nullptr,
+                        p.rope_cos + pp * p.rope_hd + d, p.rope_sin + pp * p.rope_hd + d, drow + col, drow + col + half);
+          }
+          continue;
+        }
+        tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
         if (!row_ok || col0 >= p.N || p.dbg_nostore) continue;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -428,7 +575,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
             f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
           }
-          if (d32row) {
+          if (p.silu_bwd) {
+            const __nv_bfloat16* gurow = p.GU + (int64_t)row * p.ld_gu;
+            silu_bwd_store8(f, gurow + col, gurow + p.N + col, drow + col, drow + p.N + col);
+          } else if (d32row) {
             float4* o = reinterpret_cast<float4*>(d32row + col);
             float4 a = o[0], b2 = o[1];
             a.x += f[0]; a.y += f[1]; a.z += f[2]; a.w += f[3]; b2.x += f[4]; b2.y += f[5]; b2.z += f[6]; b2.w += f[7];
@@ -464,7 +614,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, c
     LMOD_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
     attr = true;
   }
-  const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  const int tiles = ((p.M + 255) / 256) * (p.swiglu ? (p.N + 127) / 128 : (p.N + 255) / 256);
   int clusters = lmod_num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
   gemm2_tcgen05_kernel<A_MN, B_MN><<<2 * clusters, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, p);
@@ -516,9 +666,11 @@ int pick_bn(int64_t m_tiles, int64_t N) {
 // epilogue bit 0: D = bf16(D + acc) ;  d_f32_accum != null: fp32 D32 += acc (ldd applies to it) instead of the bf16 output;
 // epilogue bit 1: fused SwiGLU (B rows tile-interleaved [128 gate | 128 up] per 256; D has N/2 columns; CTA-pair kernel only);
 // epilogue bits 8..: split-K factor (fp32 atomic accumulation into D32, which the caller zero-initialises).
-extern "C" int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
-                                  int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum,
-                                  const int32_t* m_rows_dev, const int32_t* k_rows_dev, void* stream) {
+struct RopeArgs { const void* cos; const void* sin; const int64_t* pos; int hd; int cols; };
+
+static int gemm_dense(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
+                      int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum,
+                      const int32_t* m_rows_dev, const int32_t* k_rows_dev, void* stream, const RopeArgs* rope) {
   LMOD_CHECK_ARG(A && B && (D || d_f32_accum) && M > 0 && N > 0 && K > 0, "lmod_gemm_bf16: null pointer or empty problem");
   LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0 && N % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) &&
                  (!D || (uintptr_t)D % 16 == 0), "lmod_gemm_bf16: strides / N must be multiples of 8 elements and pointers 16-byte aligned (TMA)");
@@ -528,8 +680,7 @@ extern "C" int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, co
   static const int two_cta_env = getenv("LMOD_GEMM_2CTA") ? atoi(getenv("LMOD_GEMM_2CTA")) : 1;
   const int64_t tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
   const bool pair = two_cta_env && splits_req == 1 && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2;
-  if (epilogue & 2) LMOD_CHECK_ARG(pair && N % 256 == 0 && D && !d_f32_accum && !bias && !(epilogue & 1),
-                                   "lmod_gemm_bf16: the SwiGLU epilogue needs the CTA-pair kernel (>= 111 256x256 tiles) and N %% 256 == 0");
+  LMOD_CHECK_ARG(!(epilogue & 2), "lmod_gemm_bf16: epilogue bit 1 is retired -- the fused SwiGLU forward is lmod_gemm_swiglu");
   if (pair) {
     // CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 rows of A and 128 rows of B
     if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 128);
@@ -542,8 +693,8 @@ extern "C" int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, co
     p2.D = (__nv_bfloat16*)D; p2.bias = (const __nv_bfloat16*)bias; p2.D32 = d_f32_accum; p2.ldd = ldd;
     p2.M = (int)M; p2.N = (int)N; p2.K = (int)K; p2.beta = epilogue & 1; p2.splits = 1; p2.groups = 1; p2.bn = 256;
     p2.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
-    p2.swiglu = (epilogue & 2) ? 1 : 0;
     p2.m_dev = m_rows_dev; p2.k_dev = k_rows_dev;
+    if (rope) { p2.rope_cos = (const __nv_bfloat16*)rope->cos; p2.rope_sin = (const __nv_bfloat16*)rope->sin; p2.rope_pos = rope->pos; p2.rope_hd = rope->hd; p2.rope_cols = rope->cols; }
     return dispatch2(a_mn_major != 0, b_mn_major != 0, ta, tb, p2, (cudaStream_t)stream);
   }
   const int BN = pick_bn(((M + BM - 1) / BM) * splits_req, N);
@@ -559,9 +710,28 @@ extern "C" int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, co
   p.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
   p.splits = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
   p.m_dev = m_rows_dev; p.k_dev = k_rows_dev;
+  if (rope) { p.rope_cos = (const __nv_bfloat16*)rope->cos; p.rope_sin = (const __nv_bfloat16*)rope->sin; p.rope_pos = rope->pos; p.rope_hd = rope->hd; p.rope_cols = rope->cols; }
   LMOD_CHECK_ARG(p.splits == 1 || d_f32_accum, "lmod_gemm_bf16: split-K needs the fp32 accumulate output");
   const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN)) * p.splits;
   return dispatch(a_mn_major != 0, b_mn_major != 0, ta, tb, p, tiles, (cudaStream_t)stream);
+}
+
+extern "C" int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
+                                  int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum,
+                                  const int32_t* m_rows_dev, const int32_t* k_rows_dev, void* stream) {
+  return gemm_dense(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, M, N, K, bias, epilogue, d_f32_accum, m_rows_dev, k_rows_dev, stream, nullptr);
+}
+
+// q|k|v projection with the rotary embedding applied in the GEMM epilogue (Qwen2Attention: q/k/v_proj + apply_rotary_pos_emb,
+// modeling_qwen2.py:678-691,159-184): D[M, (nh+2nkv)*hd] = A W^T + bias, then every q and k head rotated with cos / sin [max_pos, hd]
+// (bf16) at position_ids[row]; v columns untouched.  Bit-identical to lmod_gemm_bf16 + lmod_rope.  hd in {64, 128}.
+extern "C" int lmod_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldb, const void* bias, void* D, int64_t ldd, int64_t M,
+                                  int64_t K, int nh, int nkv, int hd, const void* cos_table, const void* sin_table,
+                                  const int64_t* position_ids, void* stream) {
+  LMOD_CHECK_ARG(cos_table && sin_table && position_ids && nh > 0 && nkv > 0, "lmod_gemm_qkv_rope: null pointer");
+  LMOD_CHECK_ARG(hd == 64 || hd == 128, "lmod_gemm_qkv_rope: head_dim %d not fused (64 and 128 are; use lmod_gemm_bf16 + lmod_rope)", hd);
+  RopeArgs r = {cos_table, sin_table, position_ids, hd, (nh + nkv) * hd};
+  return gemm_dense(A, lda, 0, W, ldb, 0, D, ldd, M, (int64_t)(nh + 2 * nkv) * hd, K, bias, 0, nullptr, nullptr, nullptr, stream, &r);
 }
 
 extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
@@ -569,11 +739,102 @@ extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   return lmod_gemm_bf16_dyn(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, M, N, K, bias, epilogue, d_f32_accum, nullptr, nullptr, stream);
 }
 
-// 1 when lmod_gemm_bf16 would run this problem on the CTA-pair kernel (which is the one that offers the fused SwiGLU epilogue)
-extern "C" int lmod_gemm_swiglu_ok(int64_t M, int64_t N) {
+// ---- fused SwiGLU forward / backward (Qwen2MLP, modeling_qwen2.py:199-200; DeepSpeed Experts of the sparse layers) ----------------------
+// act[M, I] = bf16(bf16(silu(A W_g^T)) * (A W_u^T)) with W_gu = [W_g ; W_u] stored [2I, K] exactly as the checkpoint holds it; h1 (optional,
+// [M, 2I]) receives the bf16 pre-activations for the backward.  I % 128 == 0.
+static int swiglu_common(const void* A, int64_t lda, const void* W, int64_t ldb, void* act, int64_t ld_act, void* h1, int64_t ld_h1,
+                         const int32_t* offsets, int G, int64_t M, int64_t I, int64_t K, cudaStream_t st) {
+  LMOD_CHECK_ARG(A && W && act && M > 0 && I > 0 && K > 0, "lmod_gemm_swiglu: null pointer or empty problem");
+  LMOD_CHECK_ARG(I % 128 == 0, "lmod_gemm_swiglu: intermediate size %lld is not a multiple of 128 (use GEMM + lmod_silu_mul_fwd)", (long long)I);
+  LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ld_act % 8 == 0 && (!h1 || ld_h1 % 8 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) &&
+                 ((uintptr_t)act % 16 == 0) && (!h1 || (uintptr_t)h1 % 16 == 0), "lmod_gemm_swiglu: strides must be multiples of 8 elements, pointers 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc;
+  GemmParams p = {};
+  p.D = (__nv_bfloat16*)act; p.ldd = ld_act; p.M = (int)M; p.N = (int)I; p.K = (int)K; p.splits = 1; p.groups = G > 0 ? G : 1;
+  p.swiglu = 1; p.swiglu_I = (int)I; p.H1 = (__nv_bfloat16*)h1; p.ld_h1 = ld_h1; p.bn = 128;     // tile enumeration: 128 act columns per tile
   static const int two_cta_env = getenv("LMOD_GEMM_2CTA") ? atoi(getenv("LMOD_GEMM_2CTA")) : 1;
-  const int64_t tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
-  return (two_cta_env && N % 256 == 0 && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2) ? 1 : 0;
+  const int64_t pair_tiles = ((M + 255) / 256) * (I / 128);
+  if (!offsets && two_cta_env && pair_tiles >= (int64_t)(lmod_num_sms() / 2) * 3 / 2) {
+    rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 128);
+    if (rc) return rc;
+    rc = make_map(&tb, W, (uint64_t)K, (uint64_t)(2 * I), (uint64_t)ldb, BK, 128);
+    if (rc) return rc;
+    return dispatch2(false, false, ta, tb, p, st);
+  }
+  rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, W, (uint64_t)K, (uint64_t)((offsets ? G : 1) * 2 * I), (uint64_t)ldb, BK, 128);
+  if (rc) return rc;
+  int tiles;
+  if (offsets) {
+    p.offsets = offsets; p.b_group_rows = 2 * I;
+    tiles = (int)(((M + BM - 1) / BM + G) * (I / 128));
+  } else {
+    tiles = (int)(((M + BM - 1) / BM) * (I / 128));
+  }
+  return launch<256, false, false>(ta, tb, p, tiles, st);
+}
+
+extern "C" int lmod_gemm_swiglu(const void* A, int64_t lda, const void* W_gu, int64_t ldb, void* act, int64_t ld_act, void* h1, int64_t ld_h1,
+                                int64_t M, int64_t I, int64_t K, void* stream) {
+  return swiglu_common(A, lda, W_gu, ldb, act, ld_act, h1, ld_h1, nullptr, 0, M, I, K, (cudaStream_t)stream);
+}
+
+// grouped form on compact expert rows: A [max_rows, K], W_gu [G, 2I, K], rows of group g = [offsets[g], offsets[g+1]) (128-aligned)
+extern "C" int lmod_grouped_gemm_swiglu(const void* A, int64_t lda, const void* W_gu, int64_t ldb, void* act, int64_t ld_act, void* h1,
+                                        int64_t ld_h1, const int32_t* offsets, int G, int64_t max_rows, int64_t I, int64_t K, void* stream) {
+  LMOD_CHECK_ARG(offsets && G >= 1 && G <= MAX_GROUPS, "lmod_grouped_gemm_swiglu: bad group arguments");
+  return swiglu_common(A, lda, W_gu, ldb, act, ld_act, h1, ld_h1, offsets, G, max_rows, I, K, (cudaStream_t)stream);
+}
+
+// backward of the fused MLP input: dh1[M, 2I] = silu_mul_bwd(dY W_dn, h1) computed in the epilogue of the dgrad GEMM dY [M, K=H] x W_dn [K, I]
+// (W_dn as stored: [H, I] = MN-major B).  Grouped form: W_dn [G, K, I].
+static int silu_bwd_common(const void* dY, int64_t lda, const void* W, int64_t ldb, const void* h1, int64_t ld_h1, void* dh1, int64_t ld_dh1,
+                           const int32_t* offsets, int G, int64_t M, int64_t I, int64_t K, cudaStream_t st) {
+  LMOD_CHECK_ARG(dY && W && h1 && dh1 && M > 0 && I > 0 && K > 0 && I % 8 == 0, "lmod_gemm_silu_bwd: bad arguments");
+  LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ld_h1 % 8 == 0 && ld_dh1 % 8 == 0 && ((uintptr_t)dY % 16 == 0) && ((uintptr_t)W % 16 == 0) &&
+                 ((uintptr_t)h1 % 16 == 0) && ((uintptr_t)dh1 % 16 == 0), "lmod_gemm_silu_bwd: strides must be multiples of 8 elements, pointers 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc;
+  GemmParams p = {};
+  p.D = (__nv_bfloat16*)dh1; p.ldd = ld_dh1; p.M = (int)M; p.N = (int)I; p.K = (int)K; p.splits = 1; p.groups = G > 0 ? G : 1;
+  p.silu_bwd = 1; p.GU = (const __nv_bfloat16*)h1; p.ld_gu = ld_h1;
+  static const int two_cta_env = getenv("LMOD_GEMM_2CTA") ? atoi(getenv("LMOD_GEMM_2CTA")) : 1;
+  const int64_t tiles256 = ((M + 255) / 256) * ((I + 255) / 256);
+  if (!offsets && two_cta_env && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2) {
+    rc = make_map(&ta, dY, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 128);
+    if (rc) return rc;
+    rc = make_map(&tb, W, (uint64_t)I, (uint64_t)K, (uint64_t)ldb, 64, BK);
+    if (rc) return rc;
+    p.bn = 256;
+    return dispatch2(false, true, ta, tb, p, st);
+  }
+  const int BN = pick_bn((M + BM - 1) / BM, I);
+  p.bn = BN;
+  rc = make_map(&ta, dY, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, W, (uint64_t)I, (uint64_t)((offsets ? G : 1) * K), (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+  int tiles;
+  if (offsets) {
+    p.offsets = offsets; p.b_group_rows = K;
+    tiles = (int)(((M + BM - 1) / BM + G) * ((I + BN - 1) / BN));
+  } else {
+    tiles = (int)(((M + BM - 1) / BM) * ((I + BN - 1) / BN));
+  }
+  return dispatch(false, true, ta, tb, p, tiles, st);
+}
+
+extern "C" int lmod_gemm_silu_bwd(const void* dY, int64_t lda, const void* W_dn, int64_t ldb, const void* h1, int64_t ld_h1, void* dh1,
+                                  int64_t ld_dh1, int64_t M, int64_t I, int64_t K, void* stream) {
+  return silu_bwd_common(dY, lda, W_dn, ldb, h1, ld_h1, dh1, ld_dh1, nullptr, 0, M, I, K, (cudaStream_t)stream);
+}
+
+extern "C" int lmod_grouped_gemm_silu_bwd(const void* dY, int64_t lda, const void* W_dn, int64_t ldb, const void* h1, int64_t ld_h1, void* dh1,
+                                          int64_t ld_dh1, const int32_t* offsets, int G, int64_t max_rows, int64_t I, int64_t K, void* stream) {
+  LMOD_CHECK_ARG(offsets && G >= 1 && G <= MAX_GROUPS, "lmod_grouped_gemm_silu_bwd: bad group arguments");
+  return silu_bwd_common(dY, lda, W_dn, ldb, h1, ld_h1, dh1, ld_dh1, offsets, G, max_rows, I, K, (cudaStream_t)stream);
 }
 
 // Grouped (per-expert) GEMM on rows [offsets[g], offsets[g+1]) (device array; boundaries must be multiples of 128 for mode 0/1, of 64 for

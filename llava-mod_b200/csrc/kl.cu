@@ -335,7 +335,6 @@ __global__ void __launch_bounds__(KL_THREADS, NBUF == 2 ? 1 : KL_MIN_CTAS) kl_fu
 // (ncu dram__bytes is the check; profiles/).
 // =====================================================================================================================
 constexpr int KS_CS = 1;                 // CTAs per row (LMOD_KL_MODE=stream2 / stream4: a cluster shares a row through DSMEM)
-constexpr int KS_THREADS = 512;          // consumer threads (16 warps) + 1 producer warp
 constexpr int KS_CH = 8192;              // logit pairs per ring stage (16 KB student + 16 KB teacher)
 constexpr int KS_STAGES = 6;             // 192 KB ring
 
@@ -363,6 +362,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t phase)
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     if (!ok && ++spins > (1u << 24)) { printf("lmod kl_stream_kernel: exchange barrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
+}
+__device__ __forceinline__ void ks_wait(uint64_t* bar, uint32_t phase);
+// one lane polls, the warp sleeps at the warp barrier (512 polling threads would fight the loads for the LSU)
+__device__ __forceinline__ void ks_wait_warp(uint64_t* bar, uint32_t phase) {
+  if ((threadIdx.x & 31) == 0) ks_wait(bar, phase);
+  __syncwarp();
 }
 __device__ __forceinline__ void ks_wait(uint64_t* bar, uint32_t phase) {
   uint32_t spins = 0;
@@ -474,7 +479,8 @@ __device__ __forceinline__ bool kl_row_masks(const KlParams& p, int64_t row, int
 }
 
 // P1 / P2: how many of the 8 word-level exponential pairs of a 16-byte vector (4 words x {student, teacher}) use the polynomial in pass 1 / 2
-template <int P1, int P2>
+// KS_THREADS: consumer threads (+ one producer warp)
+template <int P1, int P2, int KS_THREADS>
 __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(16) XchgS xchg[2][KL_MAX_CS];            // [slot][source CTA]: written by the peers through DSMEM
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlP
         const int e0 = c * KS_CH, nv = min(KS_CH, len - e0) >> 3;
         const uint4* s_buf = reinterpret_cast<const uint4*>(smem_raw + (size_t)st * (KS_CH * 4));
         const uint4* t_buf = reinterpret_cast<const uint4*>(smem_raw + (size_t)st * (KS_CH * 4) + KS_CH * 2);
-        ks_wait(&full[st], (n / KS_STAGES) & 1);
+        ks_wait(&full[st], (n / KS_STAGES) & 1);      // every thread polls: one-lane polling + __syncwarp measured 25 % slower here
         for (int i = tid; i < nv; i += KS_THREADS) {
           const uint4 sv = s_buf[i], tv = t_buf[i];
           const uint32_t pmx_s = hmax2_u32(hmax2_u32(sv.x, sv.y), hmax2_u32(sv.z, sv.w));
@@ -616,8 +622,16 @@ __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlP
         float c2 = (lane < NW) ? red[5][lane] : 0.f, k = (lane < NW) ? red[6][lane] : 0.f, sl = (lane < NW) ? red[2][lane] : 0.f;
         a = warp_sum(isinf(a) ? a : a * fs); b = warp_sum(isinf(b) ? b : b * ft);
         c2 = warp_sum(c2 * ft); k = warp_sum(k * ft); sl = warp_sum(sl);
-        // publish this CTA's partials into slot [xi][rank] of EVERY CTA of the cluster (lane l -> CTA l), then arrive on its barrier
-        if ((uint32_t)lane < cs) {
+        if (cs == 1) {
+          // one CTA per row: the block totals go through shared memory and a named barrier (no DSMEM, no cluster-scope acquire -- ptxas
+          // turns that into an L1 invalidate per poll)
+          if (lane == 0) {
+            XchgS x;
+            x.ms = (len > 0) ? ms : -INFINITY; x.mt = (len > 0) ? mt : -INFINITY; x.zs = a; x.zt = b; x.a = c2; x.slab = sl; x.zk = k; x.pad = 0.f;
+            xchg[xi][0] = x;
+          }
+        } else if ((uint32_t)lane < cs) {
+          // publish this CTA's partials into slot [xi][rank] of EVERY CTA of the cluster (lane l -> CTA l), then arrive on its barrier
           const uint32_t base = mapa_u32(smem_u32(&xchg[xi][rank]), (uint32_t)lane);
           st_cluster_f32(base + 0, (len > 0) ? ms : -INFINITY); st_cluster_f32(base + 4, (len > 0) ? mt : -INFINITY);
           st_cluster_f32(base + 8, a); st_cluster_f32(base + 12, b); st_cluster_f32(base + 16, c2); st_cluster_f32(base + 20, sl);
@@ -625,7 +639,8 @@ __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlP
           mbar_arrive_cluster(mapa_u32(smem_u32(&xbar[xi]), (uint32_t)lane));
         }
       }
-      mbar_wait_cluster(&xbar[xi], xpar);
+      if (cs == 1) asm volatile("bar.sync 1, %0;" :: "n"(KS_THREADS) : "memory");
+      else mbar_wait_cluster(&xbar[xi], xpar);
       float lse_s, lse_t, xrow, slab_row;
       {
         float r_ms = -INFINITY, r_mt = -INFINITY, r_zs = 0.f, r_zt = 0.f, r_a = 0.f, r_sl = 0.f, r_zk = 0.f;
@@ -765,12 +780,12 @@ int kl_launch(KlParams p, int cs, size_t smem, int64_t n_rows, cudaStream_t stre
   return LMOD_OK;
 }
 
-template <int P1, int P2>
+template <int P1, int P2, int KS_THREADS>
 static int kl_stream_launch_t(KlParams p, int cs, int64_t n_rows, cudaStream_t stream) {
   const size_t smem = (size_t)KS_STAGES * KS_CH * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(kl_stream_kernel<P1, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LMOD_CUDA_OK(cudaFuncSetAttribute(kl_stream_kernel<P1, P2, KS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -783,28 +798,26 @@ static int kl_stream_launch_t(KlParams p, int cs, int64_t n_rows, cudaStream_t s
   static int cached[KL_MAX_CS + 1] = {0};                        // co-resident clusters per cluster size: queried once, outside any capture
   int& max_clusters = cached[cs];
   if (max_clusters <= 0) {
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_stream_kernel<P1, P2>, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kl_stream_kernel<P1, P2, KS_THREADS>, &cfg);
     if (e != cudaSuccess || max_clusters <= 0) { (void)cudaGetLastError(); max_clusters = lmod_num_sms() / cs; }
-    if (getenv("LMOD_KL_VERBOSE")) fprintf(stderr, "[lmod] kl_stream_kernel<%d,%d>: cluster %d, %zu B smem, %d co-resident clusters\n", P1, P2, cs, smem, max_clusters);
+    if (getenv("LMOD_KL_VERBOSE")) fprintf(stderr, "[lmod] kl_stream_kernel<%d,%d,%d>: cluster %d, %zu B smem, %d co-resident clusters\n", P1, P2, KS_THREADS, cs, smem, max_clusters);
   }
   int64_t ncl = n_rows < max_clusters ? n_rows : max_clusters;
   cfg.gridDim = dim3((unsigned)(ncl * cs));
-  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_stream_kernel<P1, P2>, p));
+  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kl_stream_kernel<P1, P2, KS_THREADS>, p));
   lmod_count_launch();
   return LMOD_OK;
 }
-constexpr int KS_P1 = 3, KS_P2 = 3;          // default split between the MUFU and the polynomial (profiles/kl_modes_r2.txt)
+// measured (profiles/kl_modes_r2.txt, bench-like rows): polynomial shares 0/8 0.214 ms, 2/8 0.218, 3/8 0.230, 4/8 0.244 -- the kernel is
+// not MUFU-bound, the extra FMA-pipe instructions only cost issue slots; the MUFU-only form is the default and <3,3> stays as the A/B arm
 static int kl_stream_launch(KlParams p, int cs, int64_t n_rows, cudaStream_t stream) {
-  static const char* e = getenv("LMOD_KL_POLY");       // experiments: "00", "22", "33", "44", "24", "42"
-  if (e && e[0] && e[1]) {
-    const int a = e[0] - '0', b = e[1] - '0';
-    if (a == 0 && b == 0) return kl_stream_launch_t<0, 0>(p, cs, n_rows, stream);
-    if (a == 2 && b == 2) return kl_stream_launch_t<2, 2>(p, cs, n_rows, stream);
-    if (a == 4 && b == 4) return kl_stream_launch_t<4, 4>(p, cs, n_rows, stream);
-    if (a == 2 && b == 4) return kl_stream_launch_t<2, 4>(p, cs, n_rows, stream);
-    if (a == 4 && b == 2) return kl_stream_launch_t<4, 2>(p, cs, n_rows, stream);
-  }
-  return kl_stream_launch_t<KS_P1, KS_P2>(p, cs, n_rows, stream);
+  static const char* e = getenv("LMOD_KL_POLY");       // "33": polynomial share 3/8 in both passes
+  static const char* th = getenv("LMOD_KL_THREADS");   // "256" / "768": consumer threads (default 512)
+  const int nt = th ? atoi(th) : 512;
+  if (e && e[0] == '3') return kl_stream_launch_t<3, 3, 512>(p, cs, n_rows, stream);
+  if (nt == 256) return kl_stream_launch_t<0, 0, 256>(p, cs, n_rows, stream);
+  if (nt == 768) return kl_stream_launch_t<0, 0, 768>(p, cs, n_rows, stream);
+  return kl_stream_launch_t<0, 0, 512>(p, cs, n_rows, stream);
 }
 
 extern "C" int lmod_kl_fwd_bwd_rows(const void* s_logits, int64_t ld_s, const void* t_logits, int64_t ld_t,

@@ -108,6 +108,10 @@ EncodeTiledFn get_encode() {
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { lmod_set_error("cuTensorMapEncodeTiled entry point not available"); return LMOD_ERR_CUDA; }
+  // cuTensorMapEncodeTiled is a DRIVER call: a thread that has not touched the CUDA runtime yet (autograd's backward thread, when one of
+  // our GEMMs is the first thing it runs) has no current context and gets CUDA_ERROR_INVALID_CONTEXT; a runtime call binds the primary one
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { (void)cudaFree(nullptr); ctx_bound = true; }
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstr[1] = {ld * 2};
   cuuint32_t box[2] = {box_inner, box_outer};

@@ -11,6 +11,25 @@ from ._C import call, ptr
 
 BF16 = torch.bfloat16
 
+import contextlib
+import os as _os
+
+NVTX = bool(int(_os.environ.get("LLAVAMOD_NVTX", "0")))
+
+
+@contextlib.contextmanager
+def nvtx(name):
+    """Named range for nsys / ncu timelines (LLAVAMOD_NVTX=1); a no-op otherwise (and inside CUDA-graph capture the ranges mark the
+    capture pass only, which is what identifies the kernels of a phase in `ncu --nvtx`)."""
+    if not NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
@@ -113,30 +132,111 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, ou
     return out
 
 
-def swiglu_mlp_in(x, mlp):
-    """Frozen-weight fast path of act_fn(gate_proj(x)) * up_proj(x) (modeling_qwen2.py:199-200): ONE GEMM whose epilogue applies
-    SwiGLU, so the [rows, 2I] gate|up activation is never written.  The kernel wants the fused weight tile-interleaved ([128 gate
-    rows | 128 up rows] per 256); that copy is built once per FROZEN MLP module and lives on the module (it dies with it).  It is
-    rebuilt when the fused buffer was re-pointed or written through torch (load_state_dict, .data assignment); weights the optimizer
-    updates through raw pointers never qualify, because eligibility is the member Parameters' requires_grad.
-    Returns None when the module / shape does not qualify (caller falls back to GEMM + silu_mul)."""
-    w_gu = mlp.gu_weight
-    x2 = _rows(x)
-    M = x2.shape[0]
-    N, H = w_gu.shape
-    I = N // 2
-    if mlp.gate_proj.weight.requires_grad or mlp.up_proj.weight.requires_grad or I % 128 != 0 or not _C.lib().lmod_gemm_swiglu_ok(M, N):
-        return None
-    key = (w_gu.data_ptr(), w_gu._version, mlp.gate_proj.weight._version, mlp.up_proj.weight._version)
-    ent = getattr(mlp, "_swiglu_interleaved", None)
-    if ent is None or ent[0] != key:
-        g = w_gu[:I].view(I // 128, 128, H)
-        u = w_gu[I:].view(I // 128, 128, H)
-        ent = (key, torch.stack([g, u], 1).reshape(N, H).contiguous())
-        mlp._swiglu_interleaved = ent
-    out = torch.empty(M, I, dtype=x.dtype, device=x.device)
-    call("lmod_gemm_bf16", ptr(x2), x2.stride(0), 0, ptr(ent[1]), H, 0, ptr(out), I, M, N, H, None, 2, None)
-    return out
+# Epilogue fusions run on the GEMM's 4 epilogue warps, so they pay off only when the main loop is long enough to hide them
+# (profiles/microbench_r2.txt): at the teacher's K = 4096 the fused SwiGLU forward is 8 % faster than GEMM + silu_mul (0.275 vs 0.299 ms),
+# at the student's K = 1024 it is 30 % SLOWER (49 vs 37 us; the silu-backward epilogue 58 vs 34 us) -- there the element-wise kernels,
+# which use every warp of the SM, win.  LLAVAMOD_FUSE_SWIGLU / LLAVAMOD_FUSE_ROPE: "auto" (by reduction length), "1" always, "0" never.
+FUSE_SWIGLU = _os.environ.get("LLAVAMOD_FUSE_SWIGLU", "auto")
+FUSE_ROPE = _os.environ.get("LLAVAMOD_FUSE_ROPE", "auto")
+FUSE_MIN_K = 2048
+
+
+def _fuse(mode, K):
+    return mode == "1" or (mode == "auto" and K >= FUSE_MIN_K)
+
+
+def swiglu_fusable(I, K=None, training=False):
+    """The fused SwiGLU GEMM tiles the intermediate dimension by 128 (the reference's tiny test shapes with I = 320 take GEMM + silu_mul);
+    training keeps the pre-activations, which makes the epilogue heavier still: fused only on request."""
+    if I % 128 != 0:
+        return False
+    if K is None:
+        return True
+    if training:
+        return FUSE_SWIGLU == "1"
+    return _fuse(FUSE_SWIGLU, K)
+
+
+def gemm_swiglu(x2, w_gu, save_h1):
+    """act[M,I] (, h1[M,2I]) = SwiGLU(x2 @ w_gu^T) in ONE GEMM (lmod_gemm_swiglu): w_gu is the fused gate|up weight [2I,H] as stored."""
+    _need_cuda(x2, w_gu)
+    M, H = x2.shape
+    I = w_gu.shape[0] // 2
+    act = torch.empty(M, I, dtype=x2.dtype, device=x2.device)
+    h1 = torch.empty(M, 2 * I, dtype=x2.dtype, device=x2.device) if save_h1 else None
+    call("lmod_gemm_swiglu", ptr(x2), x2.stride(0), ptr(w_gu), w_gu.stride(0), ptr(act), I, ptr(h1), 2 * I, M, I, H)
+    return act, h1
+
+
+def gemm_silu_bwd(dy2, w_dn, h1):
+    """dh1[M,2I] = silu_mul_bwd(dy2 @ w_dn, h1) in the epilogue of the down_proj dgrad (lmod_gemm_silu_bwd); w_dn [H,I] as stored."""
+    M, H = dy2.shape
+    I = w_dn.shape[1]
+    dh1 = torch.empty(M, 2 * I, dtype=dy2.dtype, device=dy2.device)
+    call("lmod_gemm_silu_bwd", ptr(dy2), dy2.stride(0), ptr(w_dn), w_dn.stride(0), ptr(h1), h1.stride(0), ptr(dh1), 2 * I, M, I, H)
+    return dh1
+
+
+def grouped_gemm_swiglu(xp, w_gu, offsets, max_rows, save_h1):
+    """Experts' gate|up + SwiGLU on compact expert rows: w_gu [E,2I,H]; returns (act [R,I], h1 [R,2I] or None)."""
+    E, I2, H = w_gu.shape
+    I = I2 // 2
+    act = torch.empty(max_rows, I, dtype=xp.dtype, device=xp.device)
+    h1 = torch.empty(max_rows, I2, dtype=xp.dtype, device=xp.device) if save_h1 else None
+    call("lmod_grouped_gemm_swiglu", ptr(xp), xp.stride(0), ptr(w_gu), w_gu.stride(1), ptr(act), I, ptr(h1), I2, ptr(offsets), E, max_rows, I, H)
+    return act, h1
+
+
+def grouped_gemm_silu_bwd(dy, w_dn, h1, offsets, max_rows):
+    """dh1 [R,2I] = silu_mul_bwd(dy @ w_dn[e], h1) per expert group; w_dn [E,H,I]."""
+    E, H, I = w_dn.shape
+    dh1 = torch.empty(max_rows, 2 * I, dtype=dy.dtype, device=dy.device)
+    call("lmod_grouped_gemm_silu_bwd", ptr(dy), dy.stride(0), ptr(w_dn), w_dn.stride(1), ptr(h1), h1.stride(0), ptr(dh1), 2 * I, ptr(offsets), E,
+         max_rows, I, H)
+    return dh1
+
+
+class MLPFn(Function):
+    """Qwen2MLP (modeling_qwen2.py:188-200) as two GEMMs: gate|up with the SwiGLU epilogue (pre-activations kept for the backward), then
+    down_proj.  Backward: the down_proj dgrad GEMM turns dY straight into d(gate)|d(up) in its epilogue; wgrads accumulate in place into
+    the flat gradient buffer views ``g_gu`` / ``g_dn`` (None = frozen)."""
+
+    @staticmethod
+    def forward(ctx, x, w_gu, w_dn, g_gu, g_dn):
+        x2 = _rows(x)
+        act, h1 = gemm_swiglu(x2, w_gu, True)
+        y = gemm(act, w_dn)
+        ctx.save_for_backward(x2, w_gu, w_dn, h1, act)
+        ctx.g = (g_gu, g_dn)
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], w_dn.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_gu, w_dn, h1, act = ctx.saved_tensors
+        g_gu, g_dn = ctx.g
+        dy2 = _c(dy).reshape(-1, dy.shape[-1])
+        dh1 = gemm_silu_bwd(dy2, w_dn, h1)
+        if g_dn is not None:
+            mm_tn_acc(dy2, act, g_dn)
+        dx = mm_nn(dh1, w_gu).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        if g_gu is not None:
+            mm_tn_acc(dh1, x2, g_gu)
+        return dx, None, None, None, None
+
+
+def mlp(x, w_gu, w_dn, g_gu=None, g_dn=None):
+    """Dense SwiGLU MLP.  Fused SwiGLU epilogues whenever the intermediate size allows; frozen / no-grad calls keep nothing."""
+    I = w_gu.shape[0] // 2
+    grad = torch.is_grad_enabled() and (x.requires_grad or g_gu is not None or g_dn is not None)
+    if swiglu_fusable(I, w_gu.shape[1], training=grad):
+        if grad:
+            return MLPFn.apply(x, w_gu, w_dn, g_gu, g_dn)
+        act, _ = gemm_swiglu(_rows(x), w_gu, False)
+        y = gemm(act, w_dn)
+        return y if x.dim() == 2 else y.view(*x.shape[:-1], w_dn.shape[0])
+    gu = linear(x, w_gu, None, g_gu, None)
+    return linear(silu_mul(gu), w_dn, None, g_dn, None)
 
 
 def grouped_gemm(a, b, out, offsets, mode, max_rows=None, accumulate=False):
@@ -375,6 +475,52 @@ class RopeFn(Function):
         return d, None, None, None, None, None, None
 
 
+class QKVRopeFn(Function):
+    """q|k|v projection + rotary embedding (modeling_qwen2.py:678-691): ONE GEMM whose epilogue adds the bias and rotates the q / k heads
+    (lmod_gemm_qkv_rope).  Backward: the transpose rotation in place on the incoming dqkv, then dgrad / wgrad / bias gradient as LinearFn."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, cos, sin, pos, nh, nkv, hd, wgrad, bgrad):
+        x2 = _rows(x)
+        M, Kd = x2.shape
+        out = torch.empty(M, w.shape[0], dtype=x.dtype, device=x.device)
+        call("lmod_gemm_qkv_rope", ptr(x2), x2.stride(0), ptr(w), w.stride(0), ptr(bias) if bias is not None else None, ptr(out), out.stride(0), M, Kd,
+             nh, nkv, hd, ptr(cos), ptr(sin), ptr(pos))
+        ctx.save_for_backward(x2, w, cos, sin, pos)
+        ctx.dims = (nh, nkv, hd)
+        ctx.g = (wgrad, bgrad)
+        ctx.xshape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        x2, w, cos, sin, pos = ctx.saved_tensors
+        nh, nkv, hd = ctx.dims
+        wgrad, bgrad = ctx.g
+        d = _c(d)                                         # the fused dq|dk|dv buffer of the attention backward: rotated back in place
+        ld = d.shape[-1]
+        call("lmod_rope", ptr(d), ld, nh, d.data_ptr() + nh * hd * 2, ld, nkv, hd, ptr(cos), ptr(sin), ptr(pos), d.numel() // ld, 1)
+        dx = mm_nn(d, w).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        if wgrad is not None:
+            mm_tn_acc(d, x2, wgrad)
+        if bgrad is not None:
+            bgrad.add_(d.sum(0).to(bgrad.dtype))
+        return (dx,) + (None,) * 10
+
+
+def qkv_rope(x, w, bias, cos, sin, pos, nh, nkv, hd, wgrad=None, bgrad=None):
+    """Fused q|k|v projection + RoPE for the head dims the epilogue is built for; other head dims (tiny test shapes) take GEMM + lmod_rope."""
+    if hd not in ATTN_HEAD_DIMS or not _fuse(FUSE_ROPE, w.shape[1]):
+        return rope_(linear(x, w, bias, wgrad, bgrad), cos, sin, pos, nh, nkv, hd)
+    if torch.is_grad_enabled() and (x.requires_grad or wgrad is not None):
+        return QKVRopeFn.apply(x, w, bias, cos, sin, pos, nh, nkv, hd, wgrad, bgrad)
+    x2 = _rows(x)
+    out = torch.empty(x2.shape[0], w.shape[0], dtype=x.dtype, device=x.device)
+    call("lmod_gemm_qkv_rope", ptr(x2), x2.stride(0), ptr(w), w.stride(0), ptr(bias) if bias is not None else None, ptr(out), out.stride(0), x2.shape[0],
+         x2.shape[1], nh, nkv, hd, ptr(cos), ptr(sin), ptr(pos))
+    return out
+
+
 def rope_(qkv, cos, sin, pos, nh, nkv, hd):
     if torch.is_grad_enabled() and qkv.requires_grad:
         return RopeFn.apply(qkv, cos, sin, pos, nh, nkv, hd)
@@ -558,9 +704,13 @@ class MoEFn(Function):
         xp, offs = r["xp"], r["offsets"]
         # only xp (and dy in the backward) are zero-filled: in the 128-aligned layout the grouped GEMM writes EVERY row below offsets[E],
         # so the padding rows of h1 / act / y come out as exact zeros (0 @ W); rows past offsets[E] are never read by a GEMM
-        h1 = torch.empty(R, I2, dtype=x.dtype, device=x.device)
-        grouped_gemm(xp, w_gu, h1, offs, 0)                            # [R,2I] = xp @ w_gu[e]^T
-        act = silu_mul(h1)                                             # [R,I]
+        ctx.fused = swiglu_fusable(I2 // 2, H, training=True)
+        if ctx.fused:
+            act, h1 = grouped_gemm_swiglu(xp, w_gu, offs, R, True)     # act [R,I], pre-activations [R,2I]: SwiGLU in the GEMM epilogue
+        else:
+            h1 = torch.empty(R, I2, dtype=x.dtype, device=x.device)
+            grouped_gemm(xp, w_gu, h1, offs, 0)                        # [R,2I] = xp @ w_gu[e]^T
+            act = silu_mul(h1)                                         # [R,I]
         y = torch.empty(R, H, dtype=x.dtype, device=x.device)
         grouped_gemm(act, w_dn, y, offs, 0)                            # [R,H] = act @ w_dn[e]^T
         out = moe_gather_combine(y, r["row"], r["w"], res)
@@ -579,11 +729,14 @@ class MoEFn(Function):
         dw = torch.empty(S, 2, dtype=torch.float32, device=dout.device)
         call("lmod_moe_combine_bwd", ptr(dout), ptr(y), ptr(row), ptr(w), S, H, ptr(dy), ptr(dw))
         g = ctx.grads
-        dact = torch.empty(R, I2 // 2, dtype=dout.dtype, device=dout.device)
-        grouped_gemm(dy, w_dn, dact, offs, 1)                          # dact = dy @ w_dn[e]
+        if ctx.fused:
+            dh1 = grouped_gemm_silu_bwd(dy, w_dn, h1, offs, R)         # d(gate)|d(up) straight from the dgrad GEMM's epilogue
+        else:
+            dact = torch.empty(R, I2 // 2, dtype=dout.dtype, device=dout.device)
+            grouped_gemm(dy, w_dn, dact, offs, 1)                      # dact = dy @ w_dn[e]
+            dh1 = silu_mul_bwd(dact, h1)
         if g is not None and g.get("w_dn") is not None:
             grouped_gemm(dy, act, g["w_dn"], offs, 2, accumulate=True)  # dW_dn[e] += dy_e^T @ act_e
-        dh1 = silu_mul_bwd(dact, h1)
         dxp = torch.empty(R, H, dtype=dout.dtype, device=dout.device)
         grouped_gemm(dh1, w_gu, dxp, offs, 1)                          # dxp = dh1 @ w_gu[e]
         if g is not None and g.get("w_gu") is not None:
@@ -605,9 +758,12 @@ def moe_forward_nograd(x, res, wg, w_gu, w_dn, noise, cf, min_cap):
     E, I2, H = w_gu.shape
     r = moe_route_scatter(_c(x), wg, noise, cf, min_cap, LAYOUT_ALIGNED)
     R = r["max_rows"]
-    h1 = torch.empty(R, I2, dtype=x.dtype, device=x.device)
-    grouped_gemm(r["xp"], w_gu, h1, r["offsets"], 0)
-    act = silu_mul(h1)
+    if swiglu_fusable(I2 // 2, H):
+        act, _ = grouped_gemm_swiglu(r["xp"], w_gu, r["offsets"], R, False)
+    else:
+        h1 = torch.empty(R, I2, dtype=x.dtype, device=x.device)
+        grouped_gemm(r["xp"], w_gu, h1, r["offsets"], 0)
+        act = silu_mul(h1)
     y = torch.empty(R, H, dtype=x.dtype, device=x.device)
     grouped_gemm(act, w_dn, y, r["offsets"], 0)
     return moe_gather_combine(y, r["row"], r["w"], _c(res)), r["meta"][0].clone(), r

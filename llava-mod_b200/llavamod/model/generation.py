@@ -73,7 +73,7 @@ def generate(model, inputs=None, images=None, attention_mask=None, max_new_token
             done |= nxt == e
         stop = bool(done.all())
         if not stop and stopping_criteria:
-            stop = all(bool(c(ids, logits)) for c in stopping_criteria)
+            stop = any(bool(c(ids, logits)) for c in stopping_criteria)      # transformers.StoppingCriteriaList.__call__: any criterion stops
         if stop:
             break
     if was_training:

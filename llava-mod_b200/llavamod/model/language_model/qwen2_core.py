@@ -275,6 +275,12 @@ class Qwen2Model(nn.Module):
         branch = None                                   # pending residual-branch output (added inside the next norm)
         l_auxes, records = [], []
         moe_i = 0
+        if moe_noise is None:
+            # DeepSpeed draws fresh Gumbel noise in every MoE layer; one draw for all layers of this forward is the same distribution
+            # with 5 launches instead of 5 per layer
+            moes = [l.mlp for l in self.layers if isinstance(l.mlp, MoE)]
+            if moes and len({m.num_experts for m in moes}) == 1:
+                moe_noise = gumbel_noise((len(moes), B * T, moes[0].num_experts), dev).unbind(0)
         for layer in self.layers:
             at = layer.self_attn
             nh, nkv, hd = at.num_heads, at.num_key_value_heads, at.head_dim
@@ -282,8 +288,7 @@ class Qwen2Model(nn.Module):
                 x, stream = K.rmsnorm(stream, layer.input_layernorm.weight, cfg.rms_norm_eps, wgrad=self.gview(layer.input_layernorm.weight))
             else:
                 x, stream = K.rmsnorm(branch, layer.input_layernorm.weight, cfg.rms_norm_eps, res=stream, wgrad=self.gview(layer.input_layernorm.weight))
-            qkv = K.linear(x, at.qkv_weight, at.qkv_bias, self.gview(at.qkv_weight), self.gview(at.qkv_bias))
-            qkv = K.rope_(qkv, cos, sin, pos, nh, nkv, hd)
+            qkv = K.qkv_rope(x, at.qkv_weight, at.qkv_bias, cos, sin, pos, nh, nkv, hd, self.gview(at.qkv_weight), self.gview(at.qkv_bias))
             attn = K.attention(qkv, B, T, nh, nkv, hd, True, None, pad)
             branch = K.linear(attn, at.o_proj.weight, None, self.gview(at.o_proj.weight), None)
             x, stream = K.rmsnorm(branch, layer.post_attention_layernorm.weight, cfg.rms_norm_eps, res=stream,
@@ -307,13 +312,7 @@ class Qwen2Model(nn.Module):
                 l_auxes.append(l_aux)
                 branch = None
             else:
-                act = None
-                if not torch.is_grad_enabled() or not (x.requires_grad or mlp.gate_proj.weight.requires_grad):
-                    act = K.swiglu_mlp_in(x, mlp)                 # frozen teacher: SwiGLU fused into the GEMM epilogue
-                if act is None:
-                    gu = K.linear(x, mlp.gu_weight, None, self.gview(mlp.gu_weight), None)
-                    act = K.silu_mul(gu)
-                branch = K.linear(act, mlp.down_proj.weight, None, self.gview(mlp.down_proj.weight), None)
+                branch = K.mlp(x, mlp.gu_weight, mlp.down_proj.weight, self.gview(mlp.gu_weight), self.gview(mlp.down_proj.weight))
         if branch is None:
             out, _ = K.rmsnorm(stream, self.norm.weight, cfg.rms_norm_eps, wgrad=self.gview(self.norm.weight))
         else:

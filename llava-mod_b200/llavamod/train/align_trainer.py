@@ -171,8 +171,10 @@ class AlignTrainer(BaseTrainer):
                                                              tower_next, nxt["splice_plan"])
                 t_logits, t_shape, rows = pipe["t_cur"], pipe["t_shape"], pipe["rows_cur"]
             else:
-                t_logits, t_shape, rows = self._teacher_forward(fwd, tower_feats, plan)
-        s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"), plan=plan)
+                with K.nvtx("teacher_forward"):
+                    t_logits, t_shape, rows = self._teacher_forward(fwd, tower_feats, plan)
+        with K.nvtx("student_forward"):
+            s = model.forward_hidden(**fwd, tower_features=tower_feats, moe_noise=inputs.get("moe_noise"), plan=plan)
         if side is not None and pipe is None:
             main.wait_stream(side)
             t_logits.record_stream(main)
@@ -183,8 +185,9 @@ class AlignTrainer(BaseTrainer):
             raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
         vocab = min(self.kd_vocab, model.config.vocab_size, t_logits.shape[-1])
         w_ce = 0.0 if self.loss_type == "only_kd" else 1.0
-        total, align_loss, ce = K.distill_head(s["hidden"], model.lm_head.weight, t_logits, labels, vocab, 1.0, w_ce,
-                                               bool(getattr(self.args, "distill_all_tokens", False)), model.lm_head_grad, rows=rows)
+        with K.nvtx("loss_head"):
+            total, align_loss, ce = K.distill_head(s["hidden"], model.lm_head.weight, t_logits, labels, vocab, 1.0, w_ce,
+                                                   bool(getattr(self.args, "distill_all_tokens", False)), model.lm_head_grad, rows=rows)
         model_moe_loss = model.moe_loss_from(s["l_aux"]) if getattr(model, "is_moe", False) else None
         # model.loss = CE (+ moe_loss)   llava_qwen1_5_moe.py:421,434
         policy_sft_loss = ce if model_moe_loss is None else ce + model_moe_loss.detach()
@@ -215,8 +218,9 @@ class AlignTrainer(BaseTrainer):
     # ---- CUDA-graph plumbing (see BaseTrainer._graphed_micro_batch) -------------------------------------------------
     def _graph_signature(self, inputs, next_inputs=None):
         images = inputs.get("images")
-        if images is None or inputs.get("moe_noise") is not None:
+        if images is None:
             return None
+        noise = inputs.get("moe_noise")
         ids = inputs["input_ids"]
         plan = inputs.get("splice_plan")
         if plan is None:
@@ -226,7 +230,8 @@ class AlignTrainer(BaseTrainer):
             return None                   # padded batches take the masked-attention path eagerly
         n_img = len(images) if not torch.is_tensor(images) else images.shape[0]
         ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
-        sig = ("align", tuple(ids.shape), tuple(plan["src"].shape), n_img, ish, plan["has_mask"], plan["has_labels"], self.loss_type)
+        sig = ("align", tuple(ids.shape), tuple(plan["src"].shape), n_img, ish, plan["has_mask"], plan["has_labels"], self.loss_type,
+               tuple(tuple(t.shape) for t in noise) if noise is not None else None)
         if next_inputs is not None and self.overlap_teacher and self.pipeline_teacher:
             nsig = self._graph_signature(next_inputs)
             if nsig == sig:

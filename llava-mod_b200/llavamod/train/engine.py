@@ -102,6 +102,7 @@ class TrainState:
         self.m32 = torch.zeros_like(self.w32) if self.n32 else None
         self.v32 = torch.zeros_like(self.w32) if self.n32 else None
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.grads_reduced = False           # set by the trainer when the all-reduce already ran inside the last micro-batch's CUDA graph
         gv = {}
         for storage, g in self._views:
             gv[id(storage)] = g
@@ -153,6 +154,7 @@ class TrainState:
 
     # ---------------------------------------------------------------------------------------------
     def zero_grad(self):
+        self.grads_reduced = False
         if self.n16:
             self.g16.zero_()
         if self.n32:
@@ -176,7 +178,9 @@ class TrainState:
         (HF Trainer divides the loss instead; same arithmetic up to bf16 rounding of the scaled loss)."""
         lr = self.lr if lr is None else lr
         self.step_count += 1
-        self.allreduce_grads()
+        if not self.grads_reduced:
+            self.allreduce_grads()
+        self.grads_reduced = False
         use_clip = self.max_grad_norm is not None and self.max_grad_norm > 0
         if use_clip:
             self.gnorm_sq.zero_()

@@ -63,6 +63,12 @@ class BaseTrainer:
         # pins its activations, so the cache is bounded (least-recently-used graph dropped) and all graphs share ONE memory pool
         self.max_graphs = int(os.environ.get("LLAVAMOD_MAX_GRAPHS", "6"))
         self._graph_pool = None
+        self._statics = {}                   # base signature -> static input buffers shared by the graphs of that signature
+        # data parallel experiment (LLAVAMOD_GRAPH_ALLREDUCE=1, OFF by default): capture the gradient all-reduce INSIDE the graph of the step's
+        # last micro-batch, behind the student's backward and ahead of the join with the teacher stream.  Measured on 2 GPUs (round 2,
+        # profiles/README.md): 320.0 ms/step against 316.6 ms with the plain blocking all-reduce after the replay -- NCCL's CTAs compete with
+        # the teacher's persistent GEMMs instead of hiding behind them -- and c10d aborts at shutdown with captured NCCL work outstanding.
+        self.graph_allreduce = bool(int(os.environ.get("LLAVAMOD_GRAPH_ALLREDUCE", "0")))
         self._suppress_store = False
         self.graph_replayed_launches = 0     # liblmod kernels executed through graph replays (not seen by the host-side counter)
 
@@ -106,15 +112,20 @@ class BaseTrainer:
         model.train()
         if self._accum == 0:
             opt.zero_grad()
+        from ..kernels import nvtx
         loss = None
-        if self.use_cuda_graphs and hasattr(self, "_graph_signature"):
-            loss = self._graphed_micro_batch(model, inputs, next_inputs)
-        if loss is None:
-            loss = self.compute_loss(model, inputs)
-            loss.backward()
+        with nvtx("micro_batch"):
+            if self.use_cuda_graphs and hasattr(self, "_graph_signature"):
+                loss = self._graphed_micro_batch(model, inputs, next_inputs)
+            if loss is None:
+                with nvtx("forward+loss"):
+                    loss = self.compute_loss(model, inputs)
+                with nvtx("backward"):
+                    loss.backward()
         self._accum += 1
         if self._accum == self.args.gradient_accumulation_steps:
-            opt.step(lr=self.current_lr(), grad_scale=1.0 / (self._accum * self.world_size))
+            with nvtx("allreduce+clip+adamw"):
+                opt.step(lr=self.current_lr(), grad_scale=1.0 / (self._accum * self.world_size))
             self._accum = 0
             self.state.global_step += 1
         return loss.detach()
@@ -132,6 +143,10 @@ class BaseTrainer:
         if sig is None:
             return None
         pipelined = isinstance(sig, tuple) and sig[-1] == "pipelined"
+        closing = (self.graph_allreduce and self.world_size > 1 and self._accum + 1 == self.args.gradient_accumulation_steps)
+        base_sig = sig
+        if closing:
+            sig = ("closing",) + tuple(sig)                 # its own graph: the same micro-batch + the captured gradient all-reduce
         ent = self._graphs.pop(sig, None)                # re-inserted below: dict order = recency
         if ent is None:
             ent = {"warm": 0}
@@ -146,8 +161,20 @@ class BaseTrainer:
             captured = [k for k, v in self._graphs.items() if "graph" in v]
             while len(captured) >= max(1, self.max_graphs):      # drop the least recently used graph with its static buffers
                 old = self._graphs.pop(captured.pop(0))
+                old_base = old.get("base")
                 old.clear()
-            static = self._graph_static_inputs(inputs, None, next_inputs, pipelined) if pipelined else self._graph_static_inputs(inputs, None)
+                if not any(v.get("base") == old_base for v in self._graphs.values()):
+                    self._statics.pop(old_base, None)
+            # the plain and the step-closing graph of one signature are captured against the SAME static buffers: they take turns on one
+            # stream of micro-batches, and the teacher's look-ahead state (logits / tower features of the next batch) must carry over
+            static = self._statics.get(base_sig)
+            if static is None:
+                static = self._graph_static_inputs(inputs, None, next_inputs, pipelined) if pipelined else self._graph_static_inputs(inputs, None)
+                self._statics[base_sig] = static
+            elif pipelined:
+                self._graph_static_inputs(inputs, static, next_inputs, True)
+            else:
+                self._graph_static_inputs(inputs, static)
             torch.cuda.synchronize()
             from .. import _C
             g = torch.cuda.CUDAGraph()
@@ -159,11 +186,13 @@ class BaseTrainer:
                 with torch.cuda.graph(g, pool=self._graph_pool):
                     loss, outputs = self.compute_loss(model, static, return_outputs=True)
                     loss.backward()
+                    if closing:
+                        self.optimizer.allreduce_grads()          # NCCL nodes in the graph, ahead of the join with the teacher stream
                     if hasattr(self, "_graph_epilogue"):
                         self._graph_epilogue(static)
             finally:
                 self._suppress_store = False
-            ent.update(graph=g, static=static, loss=loss.detach(), outputs={k: v for k, v in outputs.items()},
+            ent.update(graph=g, static=static, base=base_sig, loss=loss.detach(), outputs={k: v for k, v in outputs.items()},
                        launches=_C.launch_count() - n0)
             # the capture pass does not execute: fall through to a replay for this very batch
         if pipelined:
@@ -171,6 +200,8 @@ class BaseTrainer:
         else:
             self._graph_static_inputs(inputs, ent["static"])
         ent["graph"].replay()
+        if closing:
+            self.optimizer.grads_reduced = True              # TrainState.step() must not reduce again
         self.graph_replayed_launches += ent["launches"]
         self.store_metrics({k: (v.clone() if hasattr(v, "clone") else v) for k, v in ent["outputs"].items()}, train_eval="train")
         return ent["loss"].clone()
@@ -187,13 +218,18 @@ class BaseTrainer:
         for k, v in plan.items():
             if torch.is_tensor(v):
                 static["splice_plan"][k].copy_(v, non_blocking=True)
+        if static.get("moe_noise") is not None:           # explicit router noise (parity runs): static buffers like every other device input
+            for dst, src in zip(static["moe_noise"], inputs["moe_noise"]):
+                dst.copy_(src, non_blocking=True)
 
     def _new_static(self, inputs):
         dev = self.model.device
         images, plan = inputs["images"], inputs["splice_plan"]
         n = len(images) if not torch.is_tensor(images) else images.shape[0]
         ish = tuple(images[0].shape) if not torch.is_tensor(images) else tuple(images.shape[1:])
+        noise = inputs.get("moe_noise")
         return dict(input_ids=inputs["input_ids"], labels=inputs["labels"], attention_mask=inputs.get("attention_mask"),
+                    moe_noise=[torch.empty(tuple(t.shape), dtype=torch.float32, device=dev) for t in noise] if noise is not None else None,
                     images=torch.empty((n,) + ish, dtype=self.model.dtype, device=dev),
                     splice_plan={k: (torch.empty_like(v) if torch.is_tensor(v) else v) for k, v in plan.items()})
 

@@ -76,6 +76,33 @@ def main():
     w = torch.randn(4, 5632, 1024, device=dev).to(torch.bfloat16)
     h1 = torch.zeros(4608, 5632, device=dev, dtype=torch.bfloat16)
     timed("grouped expert gemm 4x[~1024,5632,1024]", lambda: K.grouped_gemm(xp, w, h1, offs, 0), 2.0 * 4096 * 5632 * 1024, "TFLOP/s")
+    # fused SwiGLU MLP input (gate|up GEMM + SwiGLU epilogue) and the silu-backward dgrad epilogue, against their unfused forms
+    for (M, H, I, tag, save) in [(T, 4096, 11008, "teacher", False), (T, 1024, 2816, "student dense", True)]:
+        x = torch.randn(M, H, device=dev).to(torch.bfloat16)
+        wgu = (torch.randn(2 * I, H, device=dev) * 0.02).to(torch.bfloat16)
+        wdn = (torch.randn(H, I, device=dev) * 0.02).to(torch.bfloat16)
+        timed("gemm_swiglu %s %dx%dx%d (h1 saved: %s)" % (tag, M, 2 * I, H, save), lambda: K.gemm_swiglu(x, wgu, save), 2.0 * M * 2 * I * H, "TFLOP/s")
+        timed("  unfused: gemm + silu_mul", lambda: K.silu_mul(K.gemm(x, wgu)), 2.0 * M * 2 * I * H, "TFLOP/s")
+        if save:
+            _, h1s = K.gemm_swiglu(x, wgu, True)
+            dy = torch.randn(M, H, device=dev).to(torch.bfloat16)
+            timed("gemm_silu_bwd %s %dx%dx%d" % (tag, M, I, H), lambda: K.gemm_silu_bwd(dy, wdn, h1s), 2.0 * M * I * H, "TFLOP/s")
+            timed("  unfused: dgrad gemm + silu_mul_bwd", lambda: K.silu_mul_bwd(K.gemm(dy, wdn, b_mn=True), h1s), 2.0 * M * I * H, "TFLOP/s")
+    from llavamod.model.language_model.qwen2_core import rope_tables
+    for (M, H, nh, hd, tag) in [(T, 4096, 32, 128, "teacher"), (T, 1024, 16, 64, "student")]:
+        x = torch.randn(M, H, device=dev).to(torch.bfloat16)
+        w = (torch.randn(3 * nh * hd, H, device=dev) * 0.02).to(torch.bfloat16)
+        b = torch.randn(3 * nh * hd, device=dev).to(torch.bfloat16)
+        cos, sin = rope_tables(hd, 2048, 1e6, torch.bfloat16, dev)
+        pos = torch.arange(M, device=dev)
+        K.FUSE_ROPE = "1"
+        timed("qkv GEMM + RoPE epilogue %s %dx%dx%d" % (tag, M, 3 * nh * hd, H), lambda: K.qkv_rope(x, w, b, cos, sin, pos, nh, nh, hd), 2.0 * M * 3 * nh * hd * H, "TFLOP/s")
+        K.FUSE_ROPE = "0"
+        timed("  unfused: gemm + rope", lambda: K.qkv_rope(x, w, b, cos, sin, pos, nh, nh, hd), 2.0 * M * 3 * nh * hd * H, "TFLOP/s")
+        K.FUSE_ROPE = "auto"
+    wgu_e = (torch.randn(4, 5632, 1024, device=dev) * 0.02).to(torch.bfloat16)
+    timed("grouped gemm_swiglu 4x[~1024,5632,1024]", lambda: K.grouped_gemm_swiglu(xp, wgu_e, offs, 4608, True), 2.0 * 4096 * 5632 * 1024, "TFLOP/s")
+    timed("  unfused: grouped gemm + silu_mul", lambda: K.silu_mul(K.grouped_gemm(xp, wgu_e, h1, offs, 0)), 2.0 * 4096 * 5632 * 1024, "TFLOP/s")
     # attention forward: teacher (32 heads, hd 128), student (16 heads, hd 64), CLIP (non-causal 577)
     for (B, Tt, nh, hd, causal, tag) in [(1, T, 32, 128, True, "teacher"), (1, T, 16, 64, True, "student"), (1, 577, 16, 64, False, "CLIP")]:
         qkv = torch.randn(B * Tt, 3 * nh * hd, device=dev).to(torch.bfloat16)
