@@ -397,10 +397,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 // traffic per FLOP halve.  The leader CTA (rank 0) issues tcgen05.mma.cta_group::2 (M = 256); both CTAs run a TMA producer (their
 // loads complete_tx on the LEADER's full barrier) and an epilogue over their own 128 TMEM lanes.  tcgen05.commit multicasts the
 // "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely on the leader's tmem_empty.
-constexpr int STAGES2 = 6;
-constexpr int B2_STAGE_BYTES = 128 * BK * 2;                    // half of the 256-wide B tile per CTA
-constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;    // 32 KB
-constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + 1024;
+// Two tile widths: 256 x 256 (each CTA stages 16 KB of A + 16 KB of B per k-block: 64 B/clk of shared-memory fill at full tensor rate) for
+// the big GEMMs, and 256 x 128 (16 + 8 KB: 96 B/clk, against 128 B/clk of the 1-CTA 128 x 128 tile) for the N ~ 1024 problems of the
+// 0.5B student, whose 256 x 256 tiling would leave most CTA pairs idle.
+template <int BN2> struct Cfg2 {
+  static constexpr int STAGES = (BN2 == 256) ? 6 : 8;
+  static constexpr int B_STAGE_BYTES = (BN2 / 2) * BK * 2;       // half of the B tile per CTA
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
+};
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                     // clears the CTA-pair rank bit of a shared::cluster address -> leader CTA
 
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
@@ -421,10 +426,11 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {     // arriv
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+template <int BN2, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p_in) {
   const GemmParams p = effective_extents(p_in);
+  constexpr int STAGES2 = Cfg2<BN2>::STAGES, STAGE2_BYTES = Cfg2<BN2>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES2], empty_bar[STAGES2], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -434,7 +440,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   const bool leader = rank == 0;
   const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   // SwiGLU forward: N = I and a pair's tile is 256 rows x 128 act columns (accumulator: 128 gate | 128 up columns, one half per CTA's B)
-  const int num_m = (p.M + 255) / 256, num_n = p.swiglu ? (p.N + 127) / 128 : (p.N + 255) / 256, num_k = (p.K + BK - 1) / BK;
+  const int num_m = (p.M + 255) / 256, num_n = p.swiglu ? (p.N + 127) / 128 : (p.N + BN2 - 1) / BN2, num_k = (p.K + BK - 1) / BK;
   const int ntiles = num_m * num_n;
 
   if (threadIdx.x == 0) {
@@ -445,7 +451,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_b) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_slot)), "r"(2 * BN2) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -460,7 +466,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     for (int t = cluster; t < ntiles; t += nclusters) {
       const int m0 = (t % num_m) * 256 + 128 * (int)rank;
       const int n0 = p.swiglu ? (t / num_m) * 128 + (int)rank * p.swiglu_I           // rank 0 stages the gate rows, rank 1 the matching up rows
-                              : (t / num_m) * 256 + 128 * (int)rank;
+                              : (t / num_m) * BN2 + (BN2 / 2) * (int)rank;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE2_BYTES;
@@ -476,21 +482,21 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           tma_load_2d_2sm(sb, &tma_b, kb * BK, n0, &full_bar[stage]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sb + j * (BK * 128), &tma_b, n0 + 64 * j, kb * BK, &full_bar[stage]);
+          for (int j = 0; j < BN2 / 128; ++j) tma_load_2d_2sm(sb + j * (BK * 128), &tma_b, n0 + 64 * j, kb * BK, &full_bar[stage]);
         }
         if (++stage == STAGES2) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ===================== MMA issuer (leader CTA only) =====================
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(256 >> 3) << 17) |
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN2 >> 3) << 17) |
                            ((uint32_t)(256 >> 4) << 24);
     uint32_t stage = 0, phase = 0, it = 0;
     for (int t = cluster; t < ntiles; t += nclusters, ++it) {
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
       mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 256;
+      const uint32_t d_tmem = tmem_base + acc * BN2;
       uint32_t first = 1;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait_bounded(&full_bar[stage], phase);
@@ -515,19 +521,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       mbar_wait_warp(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = (t % num_m) * 256 + 128 * (int)rank + q * 32 + lane;
-      const int n00 = (t / num_m) * 256;
+      const int n00 = (t / num_m) * BN2;
       const bool row_ok = row < p.M;
       __nv_bfloat16* drow = p.D ? p.D + (int64_t)row * p.ldd : nullptr;
       float* d32row = p.D32 ? p.D32 + (int64_t)row * p.ldd : nullptr;
-      if (p.swiglu) {
+      if (BN2 == 256 && p.swiglu) {
         // fused SwiGLU epilogue: accumulator columns [0,128) = gate, [128,256) = up of the same 128 act columns
         const int c00 = (t / num_m) * 128;
         __nv_bfloat16* h1row = p.H1 ? p.H1 + (int64_t)row * p.ld_h1 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t g[32], u[32];
-          tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), g);
-          tmem_ld32(tmem_base + acc * 256 + 128 + c * 32 + ((uint32_t)(q * 32) << 16), u);
+          tmem_ld32(tmem_base + acc * BN2 + c * 32 + ((uint32_t)(q * 32) << 16), g);
+          tmem_ld32(tmem_base + acc * BN2 + 128 + c * 32 + ((uint32_t)(q * 32) << 16), u);
           const int col0 = c00 + c * 32;
           if (!row_ok || col0 >= p.N) continue;
 #pragma unroll
@@ -542,15 +548,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         continue;
       }
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < BN2 / 32; ++c) {
         uint32_t r[32];
         const int col0 = n00 + c * 32;
         if (p.rope_cos && col0 < p.rope_cols) {
           const int hoff = col0 % p.rope_hd, half = p.rope_hd >> 1;
           if (hoff >= half) continue;
           uint32_t r2[32];
-          tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
-          tmem_ld32(tmem_base + acc * 256 + c * 32 + half + ((uint32_t)(q * 32) << 16), r2);
+          tmem_ld32(tmem_base + acc * BN2 + c * 32 + ((uint32_t)(q * 32) << 16), r);
+          tmem_ld32(tmem_base + acc * BN2 + c * 32 + half + ((uint32_t)(q * 32) << 16), r2);
           if (!row_ok) continue;
           const int64_t pp = __ldg(p.rope_pos + row);
 #pragma unroll
@@ -561,7 +567,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           }
           continue;
         }
-        tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
+        tmem_ld32(tmem_base + acc * BN2 + c * 32 + ((uint32_t)(q * 32) << 16), r);
         if (!row_ok || col0 >= p.N || p.dbg_nostore) continue;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -604,28 +610,32 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                   // the pair frees its tensor memory together
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(2 * BN2) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+template <int BN2, bool A_MN, bool B_MN>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
+    LMOD_CUDA_OK(cudaFuncSetAttribute(gemm2_tcgen05_kernel<BN2, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN2>::SMEM));
     attr = true;
   }
-  const int tiles = ((p.M + 255) / 256) * (p.swiglu ? (p.N + 127) / 128 : (p.N + 255) / 256);
+  const int tiles = ((p.M + 255) / 256) * (p.swiglu ? (p.N + 127) / 128 : (p.N + BN2 - 1) / BN2);
   int clusters = lmod_num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm2_tcgen05_kernel<A_MN, B_MN><<<2 * clusters, GEMM_THREADS, GEMM2_SMEM, st>>>(ta, tb, p);
+  gemm2_tcgen05_kernel<BN2, A_MN, B_MN><<<2 * clusters, GEMM_THREADS, Cfg2<BN2>::SMEM, st>>>(ta, tb, p);
   LMOD_LAUNCH_OK();
   return LMOD_OK;
 }
+template <int BN2>
+int dispatch2_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2<BN2, false, false>(ta, tb, p, st);
+  if (!a_mn && b_mn) return launch2<BN2, false, true>(ta, tb, p, st);
+  if (a_mn && b_mn) return launch2<BN2, true, true>(ta, tb, p, st);
+  return launch2<BN2, true, false>(ta, tb, p, st);
+}
 int dispatch2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch2<false, false>(ta, tb, p, st);
-  if (!a_mn && b_mn) return launch2<false, true>(ta, tb, p, st);
-  if (a_mn && b_mn) return launch2<true, true>(ta, tb, p, st);
-  return launch2<true, false>(ta, tb, p, st);
+  return p.bn == 128 ? dispatch2_bn<128>(a_mn, b_mn, ta, tb, p, st) : dispatch2_bn<256>(a_mn, b_mn, ta, tb, p, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -678,20 +688,29 @@ static int gemm_dense(const void* A, int64_t lda, int a_mn_major, const void* B,
   int rc;
   const int splits_req = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
   static const int two_cta_env = getenv("LMOD_GEMM_2CTA") ? atoi(getenv("LMOD_GEMM_2CTA")) : 1;
+  // measured (round 2, profiles/README.md): student dgrad 2048x1024x5632 619 vs 642 TFLOP/s, wgrad 561 vs 580, step 25.69 vs 25.92 samples/s
+  // with / without the 256 x 128 pair tiles -- the 1-CTA 128 x 128 tiles stay the default, the variant is kept behind LMOD_GEMM_PAIR128=1
+  static const int pair128_env = getenv("LMOD_GEMM_PAIR128") ? atoi(getenv("LMOD_GEMM_PAIR128")) : 0;
   const int64_t tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
-  const bool pair = two_cta_env && splits_req == 1 && tiles256 >= (int64_t)(lmod_num_sms() / 2) * 3 / 2;
+  const int64_t tiles128 = ((M + 255) / 256) * ((N + 127) / 128);
+  const int npairs = lmod_num_sms() / 2;
+  const bool pair256 = two_cta_env && splits_req == 1 && tiles256 >= (int64_t)npairs * 3 / 2;
+  // 256 x 128 pair tiles: the N ~ 1024..3072 problems (0.5B student, CLIP) whose 256 x 256 tiling cannot fill the pairs; needs most pairs busy
+  const bool pair128 = two_cta_env && pair128_env && splits_req == 1 && !pair256 && tiles128 >= (int64_t)npairs * 6 / 7;
+  const bool pair = pair256 || pair128;
   LMOD_CHECK_ARG(!(epilogue & 2), "lmod_gemm_bf16: epilogue bit 1 is retired -- the fused SwiGLU forward is lmod_gemm_swiglu");
   if (pair) {
-    // CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 rows of A and 128 rows of B
+    // CTA-pair kernel: 256 x 256 (or 256 x 128) tiles, each CTA stages 128 rows of A and half of the B tile
+    const int bn2 = pair256 ? 256 : 128;
     if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 128);
     else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
     if (rc) return rc;
-    if (!b_mn_major) rc = make_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 128);
+    if (!b_mn_major) rc = make_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, bn2 / 2);
     else rc = make_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
     if (rc) return rc;
     GemmParams p2 = {};
     p2.D = (__nv_bfloat16*)D; p2.bias = (const __nv_bfloat16*)bias; p2.D32 = d_f32_accum; p2.ldd = ldd;
-    p2.M = (int)M; p2.N = (int)N; p2.K = (int)K; p2.beta = epilogue & 1; p2.splits = 1; p2.groups = 1; p2.bn = 256;
+    p2.M = (int)M; p2.N = (int)N; p2.K = (int)K; p2.beta = epilogue & 1; p2.splits = 1; p2.groups = 1; p2.bn = bn2;
     p2.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
     p2.m_dev = m_rows_dev; p2.k_dev = k_rows_dev;
     if (rope) { p2.rope_cos = (const __nv_bfloat16*)rope->cos; p2.rope_sin = (const __nv_bfloat16*)rope->sin; p2.rope_pos = rope->pos; p2.rope_hd = rope->hd; p2.rope_cols = rope->cols; }
@@ -760,7 +779,7 @@ static int swiglu_common(const void* A, int64_t lda, const void* W, int64_t ldb,
     if (rc) return rc;
     rc = make_map(&tb, W, (uint64_t)K, (uint64_t)(2 * I), (uint64_t)ldb, BK, 128);
     if (rc) return rc;
-    return dispatch2(false, false, ta, tb, p, st);
+    return dispatch2_bn<256>(false, false, ta, tb, p, st);       // (p.bn = 128 only enumerates the 128 act columns of a tile)
   }
   rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
   if (rc) return rc;

@@ -9,8 +9,16 @@
 
 namespace {
 
+// per-block partial sums + a ticket: the LAST block to finish adds the partials in block order, so the global gradient norm (and with it
+// the clip coefficient and every weight after the step) is bit-reproducible from run to run -- a plain atomicAdd per block is not.
+// One optimizer step runs at a time per process (calls on one stream are ordered), which is what the static scratch assumes.
+constexpr int SUMSQ_MAX_BLOCKS = 4096;
+__device__ float g_sumsq_partial[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const void* __restrict__ g, int is_f32, int64_t n, float* __restrict__ out) {
   __shared__ float red[32];
+  __shared__ bool s_last;
   float a = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (is_f32) {
@@ -31,7 +39,19 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const void* __restrict__ g, 
     }
   }
   a = block_sum(a, red);
-  if (threadIdx.x == 0) atomicAdd(out, a);
+  if (threadIdx.x == 0) {
+    g_sumsq_partial[blockIdx.x] = a;
+    __threadfence();
+    s_last = (atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(&g_sumsq_partial[i]);     // fixed assignment of partials to threads
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) { out[0] += t; g_sumsq_ticket = 0u; }
+  }
 }
 
 struct AdamArgs {
@@ -68,6 +88,7 @@ extern "C" int lmod_sumsq(const void* g, int is_f32, int64_t count, float* out_a
   LMOD_CHECK_ARG(is_f32 || ((uintptr_t)g % 16 == 0), "lmod_sumsq: bf16 buffer must be 16B aligned");
   int64_t blocks = (count / 8 + 255) / 256;
   int64_t cap = (int64_t)lmod_num_sms() * 8;
+  if (cap > SUMSQ_MAX_BLOCKS) cap = SUMSQ_MAX_BLOCKS;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, is_f32, count, out_accum);

@@ -135,7 +135,8 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, ou
 # Epilogue fusions run on the GEMM's 4 epilogue warps, so they pay off only when the main loop is long enough to hide them
 # (profiles/microbench_r2.txt): at the teacher's K = 4096 the fused SwiGLU forward is 8 % faster than GEMM + silu_mul (0.275 vs 0.299 ms),
 # at the student's K = 1024 it is 30 % SLOWER (49 vs 37 us; the silu-backward epilogue 58 vs 34 us) -- there the element-wise kernels,
-# which use every warp of the SM, win.  LLAVAMOD_FUSE_SWIGLU / LLAVAMOD_FUSE_ROPE: "auto" (by reduction length), "1" always, "0" never.
+# which use every warp of the SM, win.  The (lighter) RoPE epilogue of the q|k|v projection wins at both.  LLAVAMOD_FUSE_SWIGLU: "auto" (by
+# reduction length), "1" always, "0" never; LLAVAMOD_FUSE_ROPE: "0" = GEMM + lmod_rope.
 FUSE_SWIGLU = _os.environ.get("LLAVAMOD_FUSE_SWIGLU", "auto")
 FUSE_ROPE = _os.environ.get("LLAVAMOD_FUSE_ROPE", "auto")
 FUSE_MIN_K = 2048
@@ -510,7 +511,7 @@ class QKVRopeFn(Function):
 
 def qkv_rope(x, w, bias, cos, sin, pos, nh, nkv, hd, wgrad=None, bgrad=None):
     """Fused q|k|v projection + RoPE for the head dims the epilogue is built for; other head dims (tiny test shapes) take GEMM + lmod_rope."""
-    if hd not in ATTN_HEAD_DIMS or not _fuse(FUSE_ROPE, w.shape[1]):
+    if hd not in ATTN_HEAD_DIMS or FUSE_ROPE == "0":       # the RoPE epilogue wins at every reduction length measured (K 1024: 29 vs 33 us, K 4096: 167 vs 178 us)
         return rope_(linear(x, w, bias, wgrad, bgrad), cos, sin, pos, nh, nkv, hd)
     if torch.is_grad_enabled() and (x.requires_grad or wgrad is not None):
         return QKVRopeFn.apply(x, w, bias, cos, sin, pos, nh, nkv, hd, wgrad, bgrad)

@@ -71,7 +71,8 @@ def _run_inner(rank, world, port, q, loss_kind, graphs=False):
             dist.all_reduce(t)
         losses.append(float(t) / GLOBAL)
         gnorms.append(tr.optimizer.grad_norm(1.0 / GLOBAL))
-    sd = {k: v.detach().float().cpu() for k, v in student.state_dict().items() if "image_tower" not in k}
+    # numpy, not torch tensors: torch.multiprocessing would hand CPU tensors over as shared-memory file descriptors, which die with this process
+    sd = {k: v.detach().float().cpu().numpy() for k, v in student.state_dict().items() if "image_tower" not in k}
     if rank == 0:
         q.put((losses, gnorms, sd))
     if world > 1:
@@ -88,11 +89,22 @@ def _launch(world, loss_kind, graphs=False):
     for p in procs:
         p.start()
     out = q.get(timeout=300)
-    assert out[0] != "error", out[1]
+    assert not (isinstance(out[0], str) and out[0] == "error"), out[1]
+    out = (out[0], out[1], {k: torch.from_numpy(v) for k, v in out[2].items()})
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
     return out
+
+
+def _same_weights(sd1, sd2, lr=1e-3):
+    """Adam moves every element by ~lr per step whatever the gradient's size, so an element whose gradient is rounding noise may step the
+    other way on the two sides: the allowance is 2e-3 of the tensor norm plus 10 % of the distance Adam can travel in STEPS steps.  Ranks
+    that had NOT exchanged gradients would differ by about that full distance on most elements."""
+    assert len(sd1) > 10
+    for k in sd1:
+        a, b = sd1[k], sd2[k]
+        assert (a - b).norm().item() <= 2e-3 * a.norm().item() + 0.1 * lr * STEPS * a.numel() ** 0.5, k
 
 
 @pytest.mark.parametrize("loss_kind", ["kd_lm", "sigmoid"])
@@ -104,12 +116,7 @@ def test_two_gpus_match_one_gpu_at_equal_global_batch(loss_kind):
     for s in range(STEPS):
         assert abs(l1[s] - l2[s]) < 2e-3 * abs(l1[s]) + 1e-4, (s, l1, l2)
         assert abs(g1[s] - g2[s]) < 1e-2 * abs(g1[s]) + 1e-6, (s, g1, g2)
-    moved = 0
-    for k in sd1:
-        a, b = sd1[k], sd2[k]
-        assert (a - b).norm().item() <= 2e-3 * a.norm().item() + 1e-6, k
-        moved += 1
-    assert moved > 10
+    _same_weights(sd1, sd2)
 
 
 def test_two_gpus_with_cuda_graphs_match_one_gpu():
@@ -123,5 +130,4 @@ def test_two_gpus_with_cuda_graphs_match_one_gpu():
     for s in range(STEPS):
         assert abs(l1[s] - l2[s]) < 2e-3 * abs(l1[s]) + 1e-4, (s, l1, l2)
         assert abs(g1[s] - g2[s]) < 1e-2 * abs(g1[s]) + 1e-6, (s, g1, g2)
-    for k in sd1:
-        assert (sd1[k] - sd2[k]).norm().item() <= 2e-3 * sd1[k].norm().item() + 1e-6, k
+    _same_weights(sd1, sd2)

@@ -35,9 +35,10 @@ def test_gemm_all_layouts(M, N, K, a_mn, b_mn):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("M,N,K", [(2048, 4096, 512), (1900, 3904, 520)])
+@pytest.mark.parametrize("M,N,K", [(2048, 4096, 512), (1900, 3904, 520), (2048, 1024, 2816), (5632, 1024, 2048), (2048, 3072, 1024), (1990, 1000, 520)])
 def test_gemm_two_cta_path(M, N, K, a_mn, b_mn):
-    """Problems with >= 111 256x256 tiles run on the CTA-pair (cta_group::2) kernel."""
+    """Problems with >= 111 256x256 tiles run on the CTA-pair (cta_group::2) kernel with 256x256 tiles (the 256x128 variant for the
+    N ~ 1024..3072 problems is opt-in, LMOD_GEMM_PAIR128=1, and covered when the suite runs with that switch)."""
     from llavamod import kernels as Kk
     g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
     pad = lambda n: (n + 7) // 8 * 8          # noqa: E731
