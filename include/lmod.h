@@ -242,6 +242,10 @@ int lmod_grouped_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ld
 int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
                   float softmax_scale, void* out, int64_t ld_o, float* lse, const int32_t* kv_lo, const int32_t* kv_hi,
                   void* stream);
+/* Diagnostics only (profiles/attn_trace.py; no reference counterpart): the forward kernel compiled with clock64 stamps at the pipeline
+ * hand-offs of head 0's CTAs.  trace: zero-filled int64 [ceil(seq/128)][64][16] device buffer, seq <= 4096; no padding arguments. */
+int lmod_attn_fwd_trace(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
+                        float softmax_scale, void* out, int64_t ld_o, float* lse, long long* trace, void* stream);
 /* flash-attention BACKWARD on tcgen05 (autograd of the call above): dqkv (fused dq|dk|dv, same layout as qkv) from qkv, out, dout, lse.
  * dq32_ws: fp32 [batch*seq, nh*hd] workspace (zeroed inside), dsum_ws: fp32 [batch, nh, seq] workspace; kv_lo / kv_hi as above. */
 int lmod_attn_bwd(const void* qkv, int64_t ld_qkv, const void* out, int64_t ld_o, const void* dout, int64_t ld_do,

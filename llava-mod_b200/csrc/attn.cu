@@ -36,7 +36,9 @@ struct AttnParams {
   // _unmask_unattended: they attend to every key of the row, causal mask dropped.  NULL = no padding.
   const int32_t* kv_lo;
   const int32_t* kv_hi;
+  long long* trace;      // diagnostics build only (lmod_attn_fwd_trace): clock64 stamps of head 0's CTAs, [q block][key block][16]
 };
+#define ATT_TRACE(slot) do { if (TRACE && tr) tr[(size_t)j * 16 + (slot)] = clock64(); } while (0)
 
 // packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): two lanes of a row per issue slot -- the softmax warps are issue-bound
 __device__ __forceinline__ void ffma2_bc(float& d0, float& d1, float a0, float a1, float b, float c) {     // d = a * b + c, b and c broadcast
@@ -64,7 +66,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r) {
                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
-template <int HD>
+template <int HD, bool TRACE>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnParams p) {
   constexpr int KSUB = HD / 64;                       // 64-column sub-tiles along the head dimension
@@ -103,6 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   const int nblk = (kend + BKV - 1) / BKV - jb;
   const int row_base = b * p.T;                       // row of token 0 of this batch in the fused buffer
   const int col_q = h * HD, col_k = (p.nh + hk) * HD, col_v = (p.nh + p.nkv + hk) * HD;
+  long long* tr = (TRACE && p.trace && h == 0 && b == 0) ? p.trace + (size_t)blockIdx.x * 64 * 16 : nullptr;
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
@@ -174,9 +177,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     issue_qk(0);
     for (int j = 0; j < nblk; ++j) {
       const int s = j % NST, sb = j & 1;
+      ATT_TRACE(7);
       if (j + 1 < nblk) issue_qk(j + 1);              // tensor core works on S_{j+1} while the softmax warps chew on S_j
+      ATT_TRACE(8);
       mbar_wait_bounded(&p_full[sb], (j >> 1) & 1);
+      ATT_TRACE(9);
       mbar_wait_bounded(&v_full[s], (j / NST) & 1);
+      ATT_TRACE(10);
       tc_fence_after();
       const uint32_t aV = smem_u32(sV0 + s * V_BYTES);
 #pragma unroll
@@ -187,6 +194,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       }
       umma_commit(&v_empty[s]);
       umma_commit(&pv_done);
+      ATT_TRACE(11);
     }
   } else if (warp >= 2) {
     // ===================== softmax / correction / epilogue: TWO threads per query row =====================
@@ -203,12 +211,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     int klo_r = lo, khi_r = p.causal ? min(hi, qrow + 1) : hi;
     if (all_pad || qrow < lo) { klo_r = 0; khi_r = p.T; }
     float m = -INFINITY, l0 = 0.f, l1 = 0.f;
+    if (TRACE && threadIdx.x != 64) tr = nullptr;     // stamps of warp 2 lane 0
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
+      ATT_TRACE(0);
       mbar_wait_warp(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
+      ATT_TRACE(1);
       uint32_t sv[32];
       tmem_ld32(tS0 + s * BKV + g * 32 + lane_off, sv);
+      ATT_TRACE(2);
       const int kv0 = (jb + j) * BKV + g * 32;
       const bool need_mask = (kv0 < klo_r) || (kv0 + 32 > khi_r);
       if (need_mask) {
@@ -223,6 +235,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       for (int c = 0; c < 32; c += 2) mx_loc = fmaxf(mx_loc, fmaxf(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])));
       xmax[s][g][r] = mx_loc;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      ATT_TRACE(3);
       const float mblk = fmaxf(mx_loc, xmax[s][g ^ 1][r]) * p.scale_log2;     // block max in scaled-log2 units (scale > 0); both threads of a row agree
       // lazy running max: keep the stale max while the block max stays within 2^TAU of it (P <= 2^TAU, exact in fp32 / fine in bf16); the
       // O rescale -- a TMEM round trip that also has to wait for the previous P*V -- then happens on a few early blocks only
@@ -244,6 +257,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       }
       l0 = fmaf(l0, alpha, rs0);
       l1 = fmaf(l1, alpha, rs1);
+      ATT_TRACE(4);
       if (j > 0) {
         const bool any_upd = __any_sync(0xffffffffu, upd);
         if (any_upd || j == nblk - 1) {                      // (the last block always waits: it keeps the epilogue's parity wait unambiguous)
@@ -265,11 +279,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
           }
         }
       }
+      ATT_TRACE(5);
       tmem_st16(tS0 + s * BKV + g * 16 + lane_off, pk);      // P_j (bf16x2) over the start of S_j: group g -> columns [16g, 16g+16)
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[s]);
+      ATT_TRACE(6);
     }
     const float l = l0 + l1;
     // ---- epilogue: combine the two partial row sums, normalise, store this group's half of the head dimension ----
@@ -304,16 +320,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int HD>
+template <int HD, bool TRACE>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
   constexpr int SMEM = BQ * HD * 2 + ((HD == 64) ? 4 : 2) * (2 * BKV * HD * 2) + 1024;
   static bool attr = false;
   if (!attr) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
   dim3 grid((p.T + BQ - 1) / BQ, p.nh, p.B);
-  attn_fwd_kernel<HD><<<grid, ATT_THREADS, SMEM, st>>>(tq, tkv, p);
+  attn_fwd_kernel<HD, TRACE><<<grid, ATT_THREADS, SMEM, st>>>(tq, tkv, p);
   LMOD_LAUNCH_OK();
   return LMOD_OK;
 }
@@ -323,9 +339,9 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams&
 // qkv: fused projection output [batch*seq, (nh + 2*nkv)*hd] bf16 (q heads | k heads | v heads), row stride ld_qkv.
 // out: [batch*seq, nh*hd] (row stride ld_o).  lse: [batch, nh, seq] fp32 or NULL.  hd in {64, 128}.
 // kv_lo / kv_hi: int32 [batch] device arrays, the real (un-padded) key range of every batch row, or both NULL for no padding.
-extern "C" int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
-                             float softmax_scale, void* out, int64_t ld_o, float* lse, const int32_t* kv_lo, const int32_t* kv_hi,
-                             void* stream) {
+static int attn_fwd_impl(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
+                         float softmax_scale, void* out, int64_t ld_o, float* lse, const int32_t* kv_lo, const int32_t* kv_hi,
+                         long long* trace, void* stream) {
   LMOD_CHECK_ARG((kv_lo == nullptr) == (kv_hi == nullptr), "lmod_attn_fwd: kv_lo and kv_hi come together");
   LMOD_CHECK_ARG(qkv && out && batch > 0 && seq > 0 && nh > 0 && nkv > 0 && nh % nkv == 0, "lmod_attn_fwd: bad arguments");
   LMOD_CHECK_ARG(hd == 64 || hd == 128, "lmod_attn_fwd: head_dim %d not built (64 and 128 are)", hd);
@@ -339,6 +355,24 @@ extern "C" int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int
   AttnParams p;
   p.out = (__nv_bfloat16*)out; p.lse = lse; p.ld_o = ld_o; p.B = (int)batch; p.T = (int)seq; p.nh = nh; p.nkv = nkv; p.causal = causal;
   p.scale_log2 = softmax_scale * LOG2E_F;
-  p.kv_lo = kv_lo; p.kv_hi = kv_hi;
-  return hd == 128 ? launch_attn<128>(tq, tkv, p, (cudaStream_t)stream) : launch_attn<64>(tq, tkv, p, (cudaStream_t)stream);
+  p.kv_lo = kv_lo; p.kv_hi = kv_hi; p.trace = trace;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (trace) return hd == 128 ? launch_attn<128, true>(tq, tkv, p, st) : launch_attn<64, true>(tq, tkv, p, st);
+  return hd == 128 ? launch_attn<128, false>(tq, tkv, p, st) : launch_attn<64, false>(tq, tkv, p, st);
+}
+
+extern "C" int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
+                             float softmax_scale, void* out, int64_t ld_o, float* lse, const int32_t* kv_lo, const int32_t* kv_hi,
+                             void* stream) {
+  return attn_fwd_impl(qkv, ld_qkv, batch, seq, nh, nkv, hd, causal, softmax_scale, out, ld_o, lse, kv_lo, kv_hi, nullptr, stream);
+}
+
+// Diagnostics (profiles/attn_trace.py): the same kernel compiled with clock64 stamps at the pipeline hand-offs of head 0's CTAs.
+// trace: int64 [ceil(seq/128)][64][16] device buffer, zero-filled by the caller (seq <= 4096).  Slots per key block: 0-6 softmax warp
+// (before s_full wait, after it, after tcgen05.ld, after the max exchange, after exp, before the P store, after the p_full arrive),
+// 7-11 MMA thread (top of iteration, after issuing S_{j+1}, after p_full, after v_full, after issuing P*V).
+extern "C" int lmod_attn_fwd_trace(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
+                                   float softmax_scale, void* out, int64_t ld_o, float* lse, long long* trace, void* stream) {
+  LMOD_CHECK_ARG(trace != nullptr && seq <= 4096, "lmod_attn_fwd_trace: trace buffer missing or seq > 4096");
+  return attn_fwd_impl(qkv, ld_qkv, batch, seq, nh, nkv, hd, causal, softmax_scale, out, ld_o, lse, nullptr, nullptr, trace, stream);
 }
