@@ -53,7 +53,46 @@ __device__ __forceinline__ void fmul2_bc(float& d0, float& d1, float b) {
   asm("{ .reg .b64 rb, rd; mov.b64 rd, {%0,%1}; mov.b64 rb, {%2,%2}; mul.rn.f32x2 rd, rd, rb; mov.b64 {%0,%1}, rd; }"
       : "+f"(d0), "+f"(d1) : "f"(b));
 }
-constexpr float RESCALE_TAU = 8.0f;     // lazy rescale: the running max is only raised when a block max exceeds it by > 2^8 (log2 units)
+// 2^x for a PAIR of values without the MUFU: Cody-Waite split x = n + f, f in [-0.5, 0.5], 2^f by a degree-3 polynomial (max relative error
+// 1.0e-4, a quarter of a bf16 ulp of P), 2^n by an integer add into the exponent; FFMA2 / FADD2 on the FMA pipe.  x is clamped at -126.
+__device__ __forceinline__ void exp2_poly3(float x0, float x1, float& y0, float& y1) {
+  x0 = fmaxf(x0, -126.f); x1 = fmaxf(x1, -126.f);
+  uint32_t t0, t1, p0, p1;
+  asm("{\n\t.reg .b64 x, t, n, f, p, k;\n\t"
+      "mov.b64 x, {%4, %5};\n\t"
+      "mov.b64 k, {%6, %6};\n\t"
+      "add.rn.f32x2 t, x, k;\n\t"                 // t = x + 1.5*2^23: round(x) sits in the low mantissa bits
+      "mov.b64 k, {%7, %7};\n\t"
+      "add.rn.f32x2 n, t, k;\n\t"                 // n = round(x)
+      "mov.b64 k, {%8, %8};\n\t"
+      "fma.rn.f32x2 f, n, k, x;\n\t"              // f = x - n
+      "mov.b64 p, {%9, %9};\n\t"
+      "mov.b64 k, {%10, %10};\n\t"
+      "fma.rn.f32x2 p, p, f, k;\n\t"
+      "mov.b64 k, {%11, %11};\n\t"
+      "fma.rn.f32x2 p, p, f, k;\n\t"
+      "mov.b64 k, {%12, %12};\n\t"
+      "fma.rn.f32x2 p, p, f, k;\n\t"
+      "mov.b64 {%0, %1}, t;\n\t"
+      "mov.b64 {%2, %3}, p;\n\t}"
+      : "=r"(t0), "=r"(t1), "=r"(p0), "=r"(p1)
+      : "f"(x0), "f"(x1), "f"(12582912.f), "f"(-12582912.f), "f"(-1.f), "f"(5.592203513e-02f), "f"(2.426400781e-01f), "f"(6.931210160e-01f),
+        "f"(9.999244809e-01f));
+  y0 = __uint_as_float(p0 + (t0 << 23));
+  y1 = __uint_as_float(p1 + (t1 << 23));
+}
+// P -> bf16 by TRUNCATION of 2^(x + PACK_BIAS) (one PRMT on the ALU pipe per pair) instead of a round-to-nearest conversion of 2^x (F2FP,
+// which shares the XU pipe with the exponentials -- a third of that pipe's work per key block).  PACK_BIAS = log2(1 + 2^-8 / 1.44) adds the
+// mean truncation loss back, so P stays an unbiased bf16 image of the probabilities (worst case 0.69 ulp instead of 0.5); the row sums are
+// accumulated from the same biased exponentials and divided by 2^PACK_BIAS once at the end.
+constexpr float PACK_BIAS = 0.003906f, PACK_UNBIAS = 0.99729625f;      // 2^-PACK_BIAS
+__device__ __forceinline__ uint32_t pack_trunc_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+  return d;
+}
+constexpr float RESCALE_TAU = 8.0f;
+constexpr int ATT_OPT_DEFAULT = 0;     // lazy rescale: the running max is only raised when a block max exceeds it by > 2^8 (log2 units)
 
 // instruction descriptor: F32 accumulate, BF16 inputs, M = 128, N = n ; b_mn selects the B major-ness
 __device__ __forceinline__ uint32_t attn_idesc(int n, bool b_mn) {
@@ -66,7 +105,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r) {
                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
-template <int HD, bool TRACE>
+// OPT: 0 = round-2 baseline softmax (F2FP pack, 256-thread max exchange); 1 = truncating pack + pairwise (64-thread) max exchange;
+//      2 / 3 = 1 + the exponentials of 6 / 8 of a thread's 16 pairs per block on the FMA pipe (exp2_poly3) when the block needs no mask
+template <int HD, bool TRACE, bool SPLIT, int OPT>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnParams p) {
   constexpr int KSUB = HD / 64;                       // 64-column sub-tiles along the head dimension
@@ -89,23 +130,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   uint8_t* sV0 = sK0 + NST * K_BYTES;                 // V stage s at sV0 + s*V_BYTES
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // heavier (later) causal query blocks first
+  // Grid = (heads [x 2 halves], batch, query blocks): heads vary fastest and the heavy (late) causal query blocks of ALL heads are handed out
+  // first.  The round-1 order (query blocks fastest, head by head) left the last heads' 32-block CTAs to start when most SMs had already run
+  // dry: the clock stamps of profiles/attn_trace_r2.txt put the makespan at 1.6x the balanced one for 32 heads x 16 query blocks.
   const int nqb = (p.T + BQ - 1) / BQ;
-  const int qb = p.causal ? (nqb - 1 - (int)blockIdx.x) : (int)blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int qb = p.causal ? (nqb - 1 - (int)blockIdx.z) : (int)blockIdx.z;
+  const int h = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, b = blockIdx.y;
+  const int half = SPLIT ? (int)(blockIdx.x & 1) : 0;
   const int hk = h / (p.nh / p.nkv);
   const int q0 = qb * BQ;
   int lo = 0, hi = p.T;
   if (p.kv_lo) { lo = p.kv_lo[b]; hi = p.kv_hi[b]; }
   const bool all_pad = hi <= lo;
-  // key blocks this CTA walks: [jb, jb + nblk).  A block that holds an un-masked row (no visible key) walks every key.
+  // key blocks this query block walks: [jb, jb + nblk).  A block that holds an un-masked row (no visible key) walks every key.
   int kbeg = lo, kend = p.causal ? min(hi, q0 + BQ) : hi;
   if (all_pad || q0 < lo) { kbeg = 0; kend = p.T; }
-  const int jb = kbeg / BKV;
-  const int nblk = (kend + BKV - 1) / BKV - jb;
+  int jb = kbeg / BKV;
+  int nblk = (kend + BKV - 1) / BKV - jb;
+  if (SPLIT) {
+    // SPLIT: a cluster of two CTAs shares one query block, each walks half of its key blocks (the second half holds the diagonal) and the
+    // partial (max, sum, O) of CTA 1 is merged into CTA 0 through distributed shared memory at the end.  Used when the un-split grid
+    // would not even fill the machine once (T 2048 x 16 heads: 256 CTAs for 296 slots, the 32-block CTA alone is the makespan).
+    const int n0 = nblk >> 1;
+    if (half == 0) nblk = n0; else { jb += n0; nblk -= n0; }
+  }
   const int row_base = b * p.T;                       // row of token 0 of this batch in the fused buffer
   const int col_q = h * HD, col_k = (p.nh + hk) * HD, col_v = (p.nh + p.nkv + hk) * HD;
-  long long* tr = (TRACE && p.trace && h == 0 && b == 0) ? p.trace + (size_t)blockIdx.x * 64 * 16 : nullptr;
+  long long* tr = (TRACE && p.trace && h == 0 && b == 0) ? p.trace + (size_t)blockIdx.z * 64 * 16 : nullptr;
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
@@ -123,11 +174,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   const uint32_t tmem = tmem_slot;
   const uint32_t tS0 = tmem, tO = tmem + 2 * BKV;
 
+  float m_fin = -INFINITY, lt_fin = 0.f;               // softmax threads: final (stale) running max and total row sum of this CTA's key range
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer: Q once, then the K ring and the V ring, whichever has a free slot (K first) =====================
-    mbar_expect_tx(&q_full, Q_BYTES);
+    if (nblk > 0) {
+      mbar_expect_tx(&q_full, Q_BYTES);
 #pragma unroll
-    for (int i = 0; i < KSUB; ++i) tma_load_2d(sQ + i * (BQ * 128), &tma_q, col_q + 64 * i, row_base + q0, &q_full);
+      for (int i = 0; i < KSUB; ++i) tma_load_2d(sQ + i * (BQ * 128), &tma_q, col_q + 64 * i, row_base + q0, &q_full);
+    }
     int jk = 0, jv = 0;
     uint32_t spins = 0;
     while (jk < nblk || jv < nblk) {
@@ -153,7 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
       }
       if (progressed) spins = 0;
-      else if (++spins > (1u << 26)) { printf("lmod attn_fwd_kernel: producer timeout (block %d)\n", blockIdx.x); __trap(); }
+      else if (++spins > (1u << 26)) { printf("lmod attn_fwd_kernel: producer timeout (block %d %d %d)\n", blockIdx.x, blockIdx.y, blockIdx.z); __trap(); }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -173,8 +227,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       umma_commit(&k_empty[s]);                       // the K slot is reusable as soon as these MMAs have read it
       umma_commit(&s_full[sb]);
     };
-    mbar_wait_bounded(&q_full, 0);
-    issue_qk(0);
+    if (nblk > 0) {
+      mbar_wait_bounded(&q_full, 0);
+      issue_qk(0);
+    }
     for (int j = 0; j < nblk; ++j) {
       const int s = j % NST, sb = j & 1;
       ATT_TRACE(7);
@@ -234,7 +290,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 #pragma unroll
       for (int c = 0; c < 32; c += 2) mx_loc = fmaxf(mx_loc, fmaxf(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])));
       xmax[s][g][r] = mx_loc;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (OPT >= 1) asm volatile("bar.sync %0, 64;" :: "r"(2 + q) : "memory");      // only the two warps that share these 32 rows meet
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
       ATT_TRACE(3);
       const float mblk = fmaxf(mx_loc, xmax[s][g ^ 1][r]) * p.scale_log2;     // block max in scaled-log2 units (scale > 0); both threads of a row agree
       // lazy running max: keep the stale max while the block max stays within 2^TAU of it (P <= 2^TAU, exact in fp32 / fine in bf16); the
@@ -244,16 +301,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // no visible key so far: keep everything finite (P = exp2(-inf) = 0)
       const float alpha = upd ? ex2f(m - m_new) : 1.f;       // m = -inf -> 0
       m = m_new;
-      const float neg_m = -m_use;
+      const float neg_m = (OPT >= 1) ? PACK_BIAS - m_use : -m_use;
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pk[16];
+      constexpr int NPOLY = (OPT == 2) ? 6 : (OPT == 3) ? 8 : 0;
+      if (NPOLY > 0 && !need_mask) {
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        float t0, t1;
-        ffma2_bc(t0, t1, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]), p.scale_log2, neg_m);
-        const float p0 = ex2f(t0), p1 = ex2f(t1);
-        fadd2_acc(rs0, rs1, p0, p1);
-        pk[c >> 1] = pack_bf16x2(p0, p1);
+        for (int c = 0; c < 32; c += 2) {
+          float t0, t1, p0, p1;
+          ffma2_bc(t0, t1, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]), p.scale_log2, neg_m);
+          // the polynomial pairs are spread over the loop so the two pipes stay busy side by side
+          if (((c >> 1) * NPOLY) / 16 != (((c >> 1) + 1) * NPOLY) / 16) exp2_poly3(t0, t1, p0, p1);
+          else { p0 = ex2f(t0); p1 = ex2f(t1); }
+          fadd2_acc(rs0, rs1, p0, p1);
+          pk[c >> 1] = pack_trunc_bf16x2(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float t0, t1;
+          ffma2_bc(t0, t1, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]), p.scale_log2, neg_m);
+          const float p0 = ex2f(t0), p1 = ex2f(t1);
+          fadd2_acc(rs0, rs1, p0, p1);
+          pk[c >> 1] = (OPT >= 1) ? pack_trunc_bf16x2(p0, p1) : pack_bf16x2(p0, p1);
+        }
       }
       l0 = fmaf(l0, alpha, rs0);
       l1 = fmaf(l1, alpha, rs1);
@@ -287,51 +358,132 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       if (lane == 0) mbar_arrive(&p_full[s]);
       ATT_TRACE(6);
     }
-    const float l = l0 + l1;
-    // ---- epilogue: combine the two partial row sums, normalise, store this group's half of the head dimension ----
-    xsum[g][r] = l;
+    // the two partial row sums of a row -> its total; all of this CTA's MMAs done
+    xsum[g][r] = l0 + l1;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float lt = l + xsum[g ^ 1][r];
-    mbar_wait_warp(&pv_done, (nblk - 1) & 1);
-    tc_fence_after();
+    lt_fin = ((l0 + l1) + xsum[g ^ 1][r]) * ((OPT >= 1) ? PACK_UNBIAS : 1.f);
+    m_fin = m;
+    if (nblk > 0) {
+      mbar_wait_warp(&pv_done, (nblk - 1) & 1);
+      tc_fence_after();
+    }
+  }
+  __syncwarp();
+  // ---- SPLIT: CTA 1 of the pair hands its partial (m, l, O) to CTA 0 through distributed shared memory (over CTA 0's idle Q/K/V buffers:
+  //      after the first cluster barrier every MMA and TMA load of both CTAs has completed) ----
+  constexpr int HC = HD / 2;
+  float4* xO = reinterpret_cast<float4*>(smem);         // [HD/4][BQ] float4: column quad major, row minor (conflict-free both ways)
+  float* xm = reinterpret_cast<float*>(smem + BQ * HD * 4);
+  float* xl = xm + BQ;
+  if (SPLIT) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2 && half == 1) {
+      const int q = warp & 3, g = (warp - 2) >> 2, r = q * 32 + lane;
+      const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+      uint32_t rO, rm, rl;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rO) : "r"(smem_u32(xO)));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rm) : "r"(smem_u32(xm)));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rl) : "r"(smem_u32(xl)));
+#pragma unroll
+      for (int c = 0; c < HC / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + g * HC + c * 32 + lane_off, o);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const int c4 = (g * HC + c * 32) / 4 + v;
+          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(rO + (uint32_t)(c4 * BQ + r) * 16u), "r"(o[v * 4 + 0]),
+                       "r"(o[v * 4 + 1]), "r"(o[v * 4 + 2]), "r"(o[v * 4 + 3]) : "memory");
+        }
+      }
+      if (g == 0) {
+        asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(rm + (uint32_t)r * 4u), "f"(m_fin) : "memory");
+        asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(rl + (uint32_t)r * 4u), "f"(lt_fin) : "memory");
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (warp >= 2 && half == 0) {
+    // ---- epilogue: normalise, store this group's half of the head dimension (SPLIT: after merging the partner's partial) ----
+    const int q = warp & 3, g = (warp - 2) >> 2, r = q * 32 + lane;
+    const int qrow = q0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float a0 = 1.f, a1 = 0.f, mm = m_fin, lt = lt_fin;
+    if (SPLIT) {
+      const float m1 = xm[r], l1t = xl[r];
+      mm = fmaxf(m_fin, m1);
+      a0 = (m_fin == -INFINITY) ? 0.f : ex2f(m_fin - mm);
+      a1 = (m1 == -INFINITY) ? 0.f : ex2f(m1 - mm);
+      lt = lt_fin * a0 + l1t * a1;
+    }
     const float inv = (lt > 0.f) ? 1.f / lt : 0.f;
     const bool ok = qrow < p.T;
     __nv_bfloat16* orow = p.out + (int64_t)(row_base + qrow) * p.ld_o + col_q + g * HC;
 #pragma unroll
     for (int c = 0; c < HC / 32; ++c) {
       uint32_t o[32];
-      tmem_ld32(tO + g * HC + c * 32 + lane_off, o);
+      if (!SPLIT || nblk > 0) tmem_ld32(tO + g * HC + c * 32 + lane_off, o);
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = (!SPLIT) ? __uint_as_float(o[i]) : ((a0 > 0.f && nblk > 0) ? __uint_as_float(o[i]) * a0 : 0.f);
+      if (SPLIT) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const float4 x = xO[((g * HC + c * 32) / 4 + v) * BQ + r];
+          f[v * 4 + 0] = fmaf(x.x, a1, f[v * 4 + 0]); f[v * 4 + 1] = fmaf(x.y, a1, f[v * 4 + 1]);
+          f[v * 4 + 2] = fmaf(x.z, a1, f[v * 4 + 2]); f[v * 4 + 3] = fmaf(x.w, a1, f[v * 4 + 3]);
+        }
+      }
       if (ok) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv, __uint_as_float(o[v * 8 + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv, __uint_as_float(o[v * 8 + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv, __uint_as_float(o[v * 8 + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv, __uint_as_float(o[v * 8 + 7]) * inv);
+          w.x = pack_bf16x2(f[v * 8 + 0] * inv, f[v * 8 + 1] * inv);
+          w.y = pack_bf16x2(f[v * 8 + 2] * inv, f[v * 8 + 3] * inv);
+          w.z = pack_bf16x2(f[v * 8 + 4] * inv, f[v * 8 + 5] * inv);
+          w.w = pack_bf16x2(f[v * 8 + 6] * inv, f[v * 8 + 7] * inv);
           *reinterpret_cast<uint4*>(orow + c * 32 + v * 8) = w;
         }
       }
     }
-    if (g == 0 && ok && p.lse) p.lse[((int64_t)b * p.nh + h) * p.T + qrow] = (m + lg2f(lt)) * LN2_F;
+    if (g == 0 && ok && p.lse) p.lse[((int64_t)b * p.nh + h) * p.T + qrow] = (mm + lg2f(lt)) * LN2_F;
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int HD, bool TRACE>
+template <int HD, bool TRACE, bool SPLIT, int OPT>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
   constexpr int SMEM = BQ * HD * 2 + ((HD == 64) ? 4 : 2) * (2 * BKV * HD * 2) + 1024;
+  static_assert(BQ * HD * 4 + 2 * BQ * 4 + 1024 <= SMEM, "the pair's exchange buffer lives in the Q/K/V area");
   static bool attr = false;
   if (!attr) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD, TRACE, SPLIT, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
-  dim3 grid((p.T + BQ - 1) / BQ, p.nh, p.B);
-  attn_fwd_kernel<HD, TRACE><<<grid, ATT_THREADS, SMEM, st>>>(tq, tkv, p);
-  LMOD_LAUNCH_OK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.nh * (SPLIT ? 2 : 1), p.B, (p.T + BQ - 1) / BQ);
+  cfg.blockDim = dim3(ATT_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SPLIT ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<HD, TRACE, SPLIT, OPT>, tq, tkv, p));
+  lmod_count_launch();
   return LMOD_OK;
+}
+
+// split a query block's keys over a CTA pair when the un-split grid cannot fill the machine's 2 x 148 CTA slots anyway: causal grids (uneven
+// CTAs, heavy ones first) whenever they fit in one residency; equal-sized non-causal CTAs only if the doubled grid still fits in one wave
+bool attn_split_wanted(const AttnParams& p) {
+  static int mode = -1;                                 // LMOD_ATTN_SPLIT = 0 | 1 | auto (default)
+  if (mode < 0) { const char* e = getenv("LMOD_ATTN_SPLIT"); mode = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2; }
+  if (mode != 2) return mode == 1;
+  const int slots = 2 * lmod_num_sms();
+  const long ctas = (long)p.nh * p.B * ((p.T + BQ - 1) / BQ);
+  return p.causal ? ctas <= slots : 2 * ctas <= slots;
 }
 
 }  // namespace
@@ -357,8 +509,16 @@ static int attn_fwd_impl(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t
   p.scale_log2 = softmax_scale * LOG2E_F;
   p.kv_lo = kv_lo; p.kv_hi = kv_hi; p.trace = trace;
   cudaStream_t st = (cudaStream_t)stream;
-  if (trace) return hd == 128 ? launch_attn<128, true>(tq, tkv, p, st) : launch_attn<64, true>(tq, tkv, p, st);
-  return hd == 128 ? launch_attn<128, false>(tq, tkv, p, st) : launch_attn<64, false>(tq, tkv, p, st);
+  static int opt = -1;                                  // LMOD_ATTN_OPT = 0..3 (softmax variants, see attn_fwd_kernel); default ATT_OPT_DEFAULT
+  if (opt < 0) { const char* e = getenv("LMOD_ATTN_OPT"); opt = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : ATT_OPT_DEFAULT; }
+  const bool split = !trace && attn_split_wanted(p);
+#define ATT_GO(H, T, S, O) launch_attn<H, T, S, O>(tq, tkv, p, st)
+#define ATT_BY_OPT(H, T, S) (opt == 0 ? ATT_GO(H, T, S, 0) : opt == 1 ? ATT_GO(H, T, S, 1) : opt == 2 ? ATT_GO(H, T, S, 2) : ATT_GO(H, T, S, 3))
+  if (trace) return hd == 128 ? ATT_BY_OPT(128, true, false) : ATT_BY_OPT(64, true, false);
+  if (split) return hd == 128 ? ATT_BY_OPT(128, false, true) : ATT_BY_OPT(64, false, true);
+  return hd == 128 ? ATT_BY_OPT(128, false, false) : ATT_BY_OPT(64, false, false);
+#undef ATT_BY_OPT
+#undef ATT_GO
 }
 
 extern "C" int lmod_attn_fwd(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t seq, int nh, int nkv, int hd, int causal,
