@@ -17,6 +17,7 @@
 //                                   running max moved (skipped warp-uniformly otherwise); epilogue O / l -> bf16 -> global, LSE
 // TMEM columns: S0 | S1 (64 each, P aliases its S) | O (hd).  All tensor-core work is issued by a single thread; tcgen05 executes MMAs in
 // issue order, which is what makes the S/P aliasing safe (S_{j+2} is issued after P_j V_j).
+#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace {
@@ -53,46 +54,7 @@ __device__ __forceinline__ void fmul2_bc(float& d0, float& d1, float b) {
   asm("{ .reg .b64 rb, rd; mov.b64 rd, {%0,%1}; mov.b64 rb, {%2,%2}; mul.rn.f32x2 rd, rd, rb; mov.b64 {%0,%1}, rd; }"
       : "+f"(d0), "+f"(d1) : "f"(b));
 }
-// 2^x for a PAIR of values without the MUFU: Cody-Waite split x = n + f, f in [-0.5, 0.5], 2^f by a degree-3 polynomial (max relative error
-// 1.0e-4, a quarter of a bf16 ulp of P), 2^n by an integer add into the exponent; FFMA2 / FADD2 on the FMA pipe.  x is clamped at -126.
-__device__ __forceinline__ void exp2_poly3(float x0, float x1, float& y0, float& y1) {
-  x0 = fmaxf(x0, -126.f); x1 = fmaxf(x1, -126.f);
-  uint32_t t0, t1, p0, p1;
-  asm("{\n\t.reg .b64 x, t, n, f, p, k;\n\t"
-      "mov.b64 x, {%4, %5};\n\t"
-      "mov.b64 k, {%6, %6};\n\t"
-      "add.rn.f32x2 t, x, k;\n\t"                 // t = x + 1.5*2^23: round(x) sits in the low mantissa bits
-      "mov.b64 k, {%7, %7};\n\t"
-      "add.rn.f32x2 n, t, k;\n\t"                 // n = round(x)
-      "mov.b64 k, {%8, %8};\n\t"
-      "fma.rn.f32x2 f, n, k, x;\n\t"              // f = x - n
-      "mov.b64 p, {%9, %9};\n\t"
-      "mov.b64 k, {%10, %10};\n\t"
-      "fma.rn.f32x2 p, p, f, k;\n\t"
-      "mov.b64 k, {%11, %11};\n\t"
-      "fma.rn.f32x2 p, p, f, k;\n\t"
-      "mov.b64 k, {%12, %12};\n\t"
-      "fma.rn.f32x2 p, p, f, k;\n\t"
-      "mov.b64 {%0, %1}, t;\n\t"
-      "mov.b64 {%2, %3}, p;\n\t}"
-      : "=r"(t0), "=r"(t1), "=r"(p0), "=r"(p1)
-      : "f"(x0), "f"(x1), "f"(12582912.f), "f"(-12582912.f), "f"(-1.f), "f"(5.592203513e-02f), "f"(2.426400781e-01f), "f"(6.931210160e-01f),
-        "f"(9.999244809e-01f));
-  y0 = __uint_as_float(p0 + (t0 << 23));
-  y1 = __uint_as_float(p1 + (t1 << 23));
-}
-// P -> bf16 by TRUNCATION of 2^(x + PACK_BIAS) (one PRMT on the ALU pipe per pair) instead of a round-to-nearest conversion of 2^x (F2FP,
-// which shares the XU pipe with the exponentials -- a third of that pipe's work per key block).  PACK_BIAS = log2(1 + 2^-8 / 1.44) adds the
-// mean truncation loss back, so P stays an unbiased bf16 image of the probabilities (worst case 0.69 ulp instead of 0.5); the row sums are
-// accumulated from the same biased exponentials and divided by 2^PACK_BIAS once at the end.
-constexpr float PACK_BIAS = 0.003906f, PACK_UNBIAS = 0.99729625f;      // 2^-PACK_BIAS
-__device__ __forceinline__ uint32_t pack_trunc_bf16x2(float lo, float hi) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
-  return d;
-}
-constexpr float RESCALE_TAU = 8.0f;
-constexpr int ATT_OPT_DEFAULT = 0;     // lazy rescale: the running max is only raised when a block max exceeds it by > 2^8 (log2 units)
+constexpr float RESCALE_TAU = 8.0f;     // lazy rescale: the running max is only raised when a block max exceeds it by > 2^8 (log2 units)
 
 // instruction descriptor: F32 accumulate, BF16 inputs, M = 128, N = n ; b_mn selects the B major-ness
 __device__ __forceinline__ uint32_t attn_idesc(int n, bool b_mn) {
@@ -105,10 +67,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r) {
                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
-// OPT: 0 = round-2 baseline softmax (F2FP pack, 256-thread max exchange); 1 = truncating pack + pairwise (64-thread) max exchange;
-//      2 / 3 = 1 + the exponentials of 6 / 8 of a thread's 16 pairs per block on the FMA pipe (exp2_poly3) when the block needs no mask
-template <int HD, bool TRACE, bool SPLIT, int OPT>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// REGCAP: registers capped at 80 per thread (the compiler is told to plan for 384 threads).  Registers are handed out per SM sub-partition
+// and a 10-warp CTA is accounted as 12 warps, so two CTAs are only GUARANTEED to fit next to each other at <= 65536 / (24 * 32) = 85
+// registers; the compiler's own bound for (320 threads, 2 blocks) is 102.  Measured (profiles/attn_shapes_r2.txt): hd 64 fits in 80 without
+// spilling and gains 2-8 %; hd 128 spills (stack 80 -> 136 B) and loses 20 %, so it keeps 96.
+// Tried on this loop and dropped (same file): a truncating PRMT pack instead of F2FP plus a pairwise max exchange (no change: the softmax
+// warps are bound by dependent-issue latency, not by the XU pipe) and 6-8 of 16 exponential pairs on the FMA pipe (5-7 % slower).
+template <int HD, bool TRACE, bool SPLIT, bool REGCAP>
+__global__ void __launch_bounds__(REGCAP ? 384 : ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnParams p) {
   constexpr int KSUB = HD / 64;                       // 64-column sub-tiles along the head dimension
   constexpr int Q_BYTES = BQ * HD * 2;
@@ -149,8 +115,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   int nblk = (kend + BKV - 1) / BKV - jb;
   if (SPLIT) {
     // SPLIT: a cluster of two CTAs shares one query block, each walks half of its key blocks (the second half holds the diagonal) and the
-    // partial (max, sum, O) of CTA 1 is merged into CTA 0 through distributed shared memory at the end.  Used when the un-split grid
-    // would not even fill the machine once (T 2048 x 16 heads: 256 CTAs for 296 slots, the 32-block CTA alone is the makespan).
+    // partial (max, sum, O) of CTA 1 is merged into CTA 0 through distributed shared memory at the end (see attn_split_wanted).
     const int n0 = nblk >> 1;
     if (half == 0) nblk = n0; else { jb += n0; nblk -= n0; }
   }
@@ -290,8 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 #pragma unroll
       for (int c = 0; c < 32; c += 2) mx_loc = fmaxf(mx_loc, fmaxf(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])));
       xmax[s][g][r] = mx_loc;
-      if (OPT >= 1) asm volatile("bar.sync %0, 64;" :: "r"(2 + q) : "memory");      // only the two warps that share these 32 rows meet
-      else asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       ATT_TRACE(3);
       const float mblk = fmaxf(mx_loc, xmax[s][g ^ 1][r]) * p.scale_log2;     // block max in scaled-log2 units (scale > 0); both threads of a row agree
       // lazy running max: keep the stale max while the block max stays within 2^TAU of it (P <= 2^TAU, exact in fp32 / fine in bf16); the
@@ -301,30 +265,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // no visible key so far: keep everything finite (P = exp2(-inf) = 0)
       const float alpha = upd ? ex2f(m - m_new) : 1.f;       // m = -inf -> 0
       m = m_new;
-      const float neg_m = (OPT >= 1) ? PACK_BIAS - m_use : -m_use;
+      const float neg_m = -m_use;
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pk[16];
-      constexpr int NPOLY = (OPT == 2) ? 6 : (OPT == 3) ? 8 : 0;
-      if (NPOLY > 0 && !need_mask) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float t0, t1, p0, p1;
-          ffma2_bc(t0, t1, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]), p.scale_log2, neg_m);
-          // the polynomial pairs are spread over the loop so the two pipes stay busy side by side
-          if (((c >> 1) * NPOLY) / 16 != (((c >> 1) + 1) * NPOLY) / 16) exp2_poly3(t0, t1, p0, p1);
-          else { p0 = ex2f(t0); p1 = ex2f(t1); }
-          fadd2_acc(rs0, rs1, p0, p1);
-          pk[c >> 1] = pack_trunc_bf16x2(p0, p1);
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float t0, t1;
-          ffma2_bc(t0, t1, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]), p.scale_log2, neg_m);
-          const float p0 = ex2f(t0), p1 = ex2f(t1);
-          fadd2_acc(rs0, rs1, p0, p1);
-          pk[c >> 1] = (OPT >= 1) ? pack_trunc_bf16x2(p0, p1) : pack_bf16x2(p0, p1);
-        }
+      for (int c = 0; c < 32; c += 2) {
+        float t0, t1;
+        ffma2_bc(t0, t1, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]), p.scale_log2, neg_m);
+        const float p0 = ex2f(t0), p1 = ex2f(t1);
+        fadd2_acc(rs0, rs1, p0, p1);
+        pk[c >> 1] = pack_bf16x2(p0, p1);
       }
       l0 = fmaf(l0, alpha, rs0);
       l1 = fmaf(l1, alpha, rs1);
@@ -361,7 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     // the two partial row sums of a row -> its total; all of this CTA's MMAs done
     xsum[g][r] = l0 + l1;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    lt_fin = ((l0 + l1) + xsum[g ^ 1][r]) * ((OPT >= 1) ? PACK_UNBIAS : 1.f);
+    lt_fin = ((l0 + l1) + xsum[g ^ 1][r]);
     m_fin = m;
     if (nblk > 0) {
       mbar_wait_warp(&pv_done, (nblk - 1) & 1);
@@ -452,13 +402,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int HD, bool TRACE, bool SPLIT, int OPT>
+template <int HD, bool TRACE, bool SPLIT, bool REGCAP>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
   constexpr int SMEM = BQ * HD * 2 + ((HD == 64) ? 4 : 2) * (2 * BKV * HD * 2) + 1024;
   static_assert(BQ * HD * 4 + 2 * BQ * 4 + 1024 <= SMEM, "the pair's exchange buffer lives in the Q/K/V area");
   static bool attr = false;
   if (!attr) {
-    LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD, TRACE, SPLIT, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    LMOD_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<HD, TRACE, SPLIT, REGCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -470,20 +420,31 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams&
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = SPLIT ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<HD, TRACE, SPLIT, OPT>, tq, tkv, p));
+  static bool verbose = getenv("LMOD_ATTN_VERBOSE") != nullptr;
+  if (verbose) {
+    int ncl = -1, nb = -1;
+    cudaOccupancyMaxActiveClusters(&ncl, attn_fwd_kernel<HD, TRACE, SPLIT, REGCAP>, &cfg);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_fwd_kernel<HD, TRACE, SPLIT, REGCAP>, ATT_THREADS, SMEM);
+    cudaFuncAttributes fa = {};
+    cudaFuncGetAttributes(&fa, attn_fwd_kernel<HD, TRACE, SPLIT, REGCAP>);
+    fprintf(stderr, "[lmod] attn_fwd_kernel<%d,%d,%d,%d> grid (%u,%u,%u) cluster %d: %d co-resident clusters, %d CTAs/SM (regs %d, static smem %zu, dynamic %d, local %zu)\n",
+            HD, (int)TRACE, (int)SPLIT, (int)REGCAP, cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z, SPLIT ? 2 : 1, ncl, nb, fa.numRegs, fa.sharedSizeBytes, SMEM,
+            fa.localSizeBytes);
+    verbose = false;
+  }
+  LMOD_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<HD, TRACE, SPLIT, REGCAP>, tq, tkv, p));
   lmod_count_launch();
   return LMOD_OK;
 }
 
-// split a query block's keys over a CTA pair when the un-split grid cannot fill the machine's 2 x 148 CTA slots anyway: causal grids (uneven
-// CTAs, heavy ones first) whenever they fit in one residency; equal-sized non-causal CTAs only if the doubled grid still fits in one wave
-bool attn_split_wanted(const AttnParams& p) {
-  static int mode = -1;                                 // LMOD_ATTN_SPLIT = 0 | 1 | auto (default)
-  if (mode < 0) { const char* e = getenv("LMOD_ATTN_SPLIT"); mode = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2; }
-  if (mode != 2) return mode == 1;
-  const int slots = 2 * lmod_num_sms();
-  const long ctas = (long)p.nh * p.B * ((p.T + BQ - 1) / BQ);
-  return p.causal ? ctas <= slots : 2 * ctas <= slots;
+// LMOD_ATTN_SPLIT=1: split every query block's keys over a CTA pair (SPLIT above).  Off by default: measured on the shapes it was built for
+// (T 2048 x 16 heads, the CLIP tower) it changes nothing -- cluster launches lose the second co-resident CTA per SM, which costs what the
+// shorter critical path gains (profiles/attn_shapes_r2.txt).  Kept because it is verified (tests/test_attn_gpu.py runs it in a child
+// process) and is the building block for a decode-shaped grid.
+bool attn_split_wanted(const AttnParams&) {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("LMOD_ATTN_SPLIT"); mode = (e && e[0] == '1') ? 1 : 0; }
+  return mode == 1;
 }
 
 }  // namespace
@@ -509,15 +470,14 @@ static int attn_fwd_impl(const void* qkv, int64_t ld_qkv, int64_t batch, int64_t
   p.scale_log2 = softmax_scale * LOG2E_F;
   p.kv_lo = kv_lo; p.kv_hi = kv_hi; p.trace = trace;
   cudaStream_t st = (cudaStream_t)stream;
-  static int opt = -1;                                  // LMOD_ATTN_OPT = 0..3 (softmax variants, see attn_fwd_kernel); default ATT_OPT_DEFAULT
-  if (opt < 0) { const char* e = getenv("LMOD_ATTN_OPT"); opt = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : ATT_OPT_DEFAULT; }
+  static int cap = -1;                                  // LMOD_ATTN_REGCAP = 0 | 1 overrides the per-head-dim default (hd 64: capped, hd 128: not)
+  if (cap < 0) { const char* e = getenv("LMOD_ATTN_REGCAP"); cap = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 2; }
+  const bool regcap = cap == 2 ? hd == 64 : cap == 1;
   const bool split = !trace && attn_split_wanted(p);
-#define ATT_GO(H, T, S, O) launch_attn<H, T, S, O>(tq, tkv, p, st)
-#define ATT_BY_OPT(H, T, S) (opt == 0 ? ATT_GO(H, T, S, 0) : opt == 1 ? ATT_GO(H, T, S, 1) : opt == 2 ? ATT_GO(H, T, S, 2) : ATT_GO(H, T, S, 3))
-  if (trace) return hd == 128 ? ATT_BY_OPT(128, true, false) : ATT_BY_OPT(64, true, false);
-  if (split) return hd == 128 ? ATT_BY_OPT(128, false, true) : ATT_BY_OPT(64, false, true);
-  return hd == 128 ? ATT_BY_OPT(128, false, false) : ATT_BY_OPT(64, false, false);
-#undef ATT_BY_OPT
+#define ATT_GO(H, T, S) (regcap ? launch_attn<H, T, S, true>(tq, tkv, p, st) : launch_attn<H, T, S, false>(tq, tkv, p, st))
+  if (trace) return hd == 128 ? ATT_GO(128, true, false) : ATT_GO(64, true, false);
+  if (split) return hd == 128 ? ATT_GO(128, false, true) : ATT_GO(64, false, true);
+  return hd == 128 ? ATT_GO(128, false, false) : ATT_GO(64, false, false);
 #undef ATT_GO
 }
 

@@ -183,3 +183,17 @@ def test_attn_throughput_report():
             torch.cuda.synchronize()
             res.append(fl * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
         print(f"attn fwd B{B} T{T} nh{nh} hd{hd} causal={causal}: lmod tcgen05 {res[0]:.0f} TFLOP/s, flash-attn2 {res[1]:.0f} TFLOP/s")
+
+
+@pytest.mark.parametrize("env", [{"LMOD_ATTN_SPLIT": "1"}, {"LMOD_ATTN_REGCAP": "0"}, {"LMOD_ATTN_REGCAP": "1", "LMOD_ATTN_SPLIT": "1"}])
+def test_attn_fwd_build_variants_in_a_child_process(env):
+    """The forward kernel has compile-time variants the library picks once per process: the CTA-pair key split with its DSMEM merge
+    (LMOD_ATTN_SPLIT=1, off by default) and the 80-register build (default for head_dim 64 only).  Run the forward / padded-batch parity
+    cases above under each non-default choice in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_attn_gpu.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "matches_sdpa or padded_batch or other_head_dims"], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
