@@ -6,3 +6,4 @@ from .language_model.llava_qwen1_5_moe import (LLaVAMoDQwen1_5ForCausalLM, LLaVA
 from .language_model.llava_qwen2 import LlavaQwen2ForCausalLM, LlavaQwen2Config  # noqa: F401
 from .language_model.llava_qwen2_moe import (LLaVAMoDQwen2ForCausalLM, LLaVAMoDQwen2Config,  # noqa: F401
                                               LLaVAMoDQwen2ForCausalLMFineTune, EvalLLaVAMoDQwen2ForCausalLM)
+from .auto import AutoConfig, AutoModelForCausalLM  # noqa: F401,E402

@@ -15,3 +15,10 @@ class LlavaQwen1_5Model(LlavaQwenModelBase):
 class LlavaQwen1_5ForCausalLM(LlavaQwenForCausalLMBase):
     config_class = LlavaQwen1_5Config
     model_class = LlavaQwen1_5Model
+
+
+# the reference's auto-factory registrations (llava_qwen1_5.py:170-171), on this package's own registry
+from ..auto import AutoConfig, AutoModelForCausalLM  # noqa: E402
+
+AutoConfig.register("llava_qwen1_5", LlavaQwen1_5Config)
+AutoModelForCausalLM.register(LlavaQwen1_5Config, LlavaQwen1_5ForCausalLM)

@@ -24,3 +24,12 @@ class EvalLLaVAMoDQwen1_5ForCausalLM(LLaVAMoDFineTuneBase):
     """Inference-time class: same construction from config.moe; routing uses eval_capacity_factor in eval()."""
     config_class = LLaVAMoDQwen1_5Config
     model_class = LLaVAMoDQwen1_5Model
+
+
+# the reference's auto-factory registrations (llava_qwen1_5_moe.py:684-687), on this package's own registry
+from ..auto import AutoConfig, AutoModelForCausalLM  # noqa: E402
+
+AutoConfig.register("moe_llava_qwen1_5", LLaVAMoDQwen1_5Config)
+AutoModelForCausalLM.register(LLaVAMoDQwen1_5Config, LLaVAMoDQwen1_5ForCausalLM)
+AutoModelForCausalLM.register(LLaVAMoDQwen1_5Config, LLaVAMoDQwen1_5ForCausalLMFineTune)
+AutoModelForCausalLM.register(LLaVAMoDQwen1_5Config, EvalLLaVAMoDQwen1_5ForCausalLM)

@@ -15,3 +15,10 @@ class LlavaQwen2Model(LlavaQwenModelBase):
 class LlavaQwen2ForCausalLM(LlavaQwenForCausalLMBase):
     config_class = LlavaQwen2Config
     model_class = LlavaQwen2Model
+
+
+# the reference's auto-factory registrations (llava_qwen2.py:133-134), on this package's own registry
+from ..auto import AutoConfig, AutoModelForCausalLM  # noqa: E402
+
+AutoConfig.register("llava_qwen2", LlavaQwen2Config)
+AutoModelForCausalLM.register(LlavaQwen2Config, LlavaQwen2ForCausalLM)

@@ -24,3 +24,12 @@ class EvalLLaVAMoDQwen2ForCausalLM(LLaVAMoDFineTuneBase):
     """Inference-time class: same construction from config.moe; routing uses eval_capacity_factor in eval()."""
     config_class = LLaVAMoDQwen2Config
     model_class = LLaVAMoDQwen2Model
+
+
+# the reference's auto-factory registrations (llava_qwen2_moe.py:684-687), on this package's own registry
+from ..auto import AutoConfig, AutoModelForCausalLM  # noqa: E402
+
+AutoConfig.register("moe_llava_qwen2", LLaVAMoDQwen2Config)
+AutoModelForCausalLM.register(LLaVAMoDQwen2Config, LLaVAMoDQwen2ForCausalLM)
+AutoModelForCausalLM.register(LLaVAMoDQwen2Config, LLaVAMoDQwen2ForCausalLMFineTune)
+AutoModelForCausalLM.register(LLaVAMoDQwen2Config, EvalLLaVAMoDQwen2ForCausalLM)

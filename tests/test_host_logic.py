@@ -108,3 +108,26 @@ def test_moe_checkpoint_keys_and_upcycling():
     m2 = LLaVAMoDQwen1_5ForCausalLMFineTune.from_pretrained(d, device="cpu", torch_dtype=torch.float32)
     for k, v in m.state_dict().items():
         assert torch.equal(v, m2.state_dict()[k]), k
+
+
+def test_auto_factories_resolve_the_registered_families(tmp_path):
+    """llava_qwen1_5.py:170-171 / llava_qwen2.py:133-134 / llava_qwen*_moe.py:684-687: `AutoConfig.from_pretrained(dir)` picks the config class
+    from config.json's model_type; the model class registered LAST for a config is the one the factory builds (the Eval class for MoE)."""
+    import llavamod.model as M
+    from llavamod.model.auto import _MODELS
+    for mt, cfg_cls, model_cls in (("llava_qwen1_5", M.LlavaQwen1_5Config, M.LlavaQwen1_5ForCausalLM),
+                                   ("llava_qwen2", M.LlavaQwen2Config, M.LlavaQwen2ForCausalLM),
+                                   ("moe_llava_qwen1_5", M.LLaVAMoDQwen1_5Config, M.EvalLLaVAMoDQwen1_5ForCausalLM),
+                                   ("moe_llava_qwen2", M.LLaVAMoDQwen2Config, M.EvalLLaVAMoDQwen2ForCausalLM)):
+        d = tmp_path / mt
+        cfg_cls(vocab_size=64, hidden_size=32, intermediate_size=48, num_hidden_layers=1, num_attention_heads=2).save_pretrained(str(d))
+        cfg = M.AutoConfig.from_pretrained(str(d))
+        assert type(cfg) is cfg_cls and cfg.model_type == mt and cfg.hidden_size == 32
+        assert _MODELS[cfg_cls] is model_cls
+        assert type(M.AutoConfig.for_model(mt, hidden_size=16)) is cfg_cls
+    (tmp_path / "other").mkdir()
+    (tmp_path / "other" / "config.json").write_text('{"model_type": "llama"}')
+    with pytest.raises(ValueError):
+        M.AutoConfig.from_pretrained(str(tmp_path / "other"))
+    with pytest.raises(ValueError):
+        M.AutoConfig.register("not_its_type", M.LlavaQwen2Config)
