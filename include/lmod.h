@@ -215,6 +215,12 @@ int lmod_gemm_bf16_dyn(const void* A, int64_t lda, int a_mn_major, const void* B
  * Grouped form: compact expert rows, W_gu [G, 2I, K], offsets from lmod_moe_route_scatter (128-row aligned).
  * Backward: lmod_gemm_silu_bwd computes dh1[M, 2I] = silu_mul_bwd(dY W_dn, h1) in the epilogue of the down_proj dgrad GEMM
  * (dY [M, K], W_dn [K, I] as stored), so the [M, I] dact tensor is never written; grouped form W_dn [G, K, I]. */
+/* D[M,N] = bf16( bf16(A W^T + bias) + R ): a projection written straight into the residual stream -- o_proj / down_proj of
+ * Qwen2DecoderLayer.forward (`hidden_states = residual + hidden_states`, modeling_qwen2.py:796,808) and out_proj / fc2 of the CLIP encoder
+ * layers.  The GEMM output is rounded to bf16 before the add, as the reference materialises it: bit-identical to lmod_gemm_bf16 + lmod_add.
+ * A [M,K], W [N,K] (both K-major), bias [N] or NULL, R [M,N] (row stride ld_r); D may alias R. */
+int lmod_gemm_residual(const void* A, int64_t lda, const void* W, int64_t ldb, const void* bias, const void* R, int64_t ld_r,
+                       void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, void* stream);
 /* q|k|v projection with apply_rotary_pos_emb (modeling_qwen2.py:678-691,159-184) in the GEMM epilogue: D[M,(nh+2nkv)*hd] = A W^T + bias,
  * q and k heads rotated with cos/sin [max_pos, hd] (bf16) at position_ids[row], v untouched.  Bit-identical to lmod_gemm_bf16 followed by
  * lmod_rope (same bf16 roundings).  hd in {64,128}. */

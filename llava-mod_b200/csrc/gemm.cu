@@ -59,6 +59,10 @@ struct GemmParams {
   const __nv_bfloat16* rope_sin;
   const int64_t* rope_pos;
   int rope_hd, rope_cols;
+  // fused residual add (Qwen2DecoderLayer `hidden_states = residual + hidden_states`, modeling_qwen2.py:796,808; CLIP encoder layers):
+  // D = bf16( bf16(acc + bias) + R ) -- the GEMM output is rounded to bf16 first, exactly as the reference materialises it before its add
+  const __nv_bfloat16* R;
+  int64_t ld_r;
   int dbg_nostore;                 // timing experiments only (LMOD_GEMM_NOSTORE=1): epilogue drains TMEM but does not write D
   // grouped (experts): row ranges from `offsets` (device), B / D32 advance per group
   const int32_t* offsets;          // [groups+1] or null
@@ -375,6 +379,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               f[0] += bf16lo(old.x); f[1] += bf16hi(old.x); f[2] += bf16lo(old.y); f[3] += bf16hi(old.y);
               f[4] += bf16lo(old.z); f[5] += bf16hi(old.z); f[6] += bf16lo(old.w); f[7] += bf16hi(old.w);
             }
+            if (p.R) {
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.R + (int64_t)row * p.ld_r + col));
+              f[0] = bf16_round(f[0]) + bf16lo(rr.x); f[1] = bf16_round(f[1]) + bf16hi(rr.x);
+              f[2] = bf16_round(f[2]) + bf16lo(rr.y); f[3] = bf16_round(f[3]) + bf16hi(rr.y);
+              f[4] = bf16_round(f[4]) + bf16lo(rr.z); f[5] = bf16_round(f[5]) + bf16hi(rr.z);
+              f[6] = bf16_round(f[6]) + bf16lo(rr.w); f[7] = bf16_round(f[7]) + bf16hi(rr.w);
+            }
             uint4 w;
             w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
             *o = w;
@@ -596,6 +607,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
               f[0] += bf16lo(old.x); f[1] += bf16hi(old.x); f[2] += bf16lo(old.y); f[3] += bf16hi(old.y);
               f[4] += bf16lo(old.z); f[5] += bf16hi(old.z); f[6] += bf16lo(old.w); f[7] += bf16hi(old.w);
             }
+            if (p.R) {
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.R + (int64_t)row * p.ld_r + col));
+              f[0] = bf16_round(f[0]) + bf16lo(rr.x); f[1] = bf16_round(f[1]) + bf16hi(rr.x);
+              f[2] = bf16_round(f[2]) + bf16lo(rr.y); f[3] = bf16_round(f[3]) + bf16hi(rr.y);
+              f[4] = bf16_round(f[4]) + bf16lo(rr.z); f[5] = bf16_round(f[5]) + bf16hi(rr.z);
+              f[6] = bf16_round(f[6]) + bf16lo(rr.w); f[7] = bf16_round(f[7]) + bf16hi(rr.w);
+            }
             uint4 w;
             w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
             *o = w;
@@ -677,10 +695,11 @@ int pick_bn(int64_t m_tiles, int64_t N) {
 // epilogue bit 1: fused SwiGLU (B rows tile-interleaved [128 gate | 128 up] per 256; D has N/2 columns; CTA-pair kernel only);
 // epilogue bits 8..: split-K factor (fp32 atomic accumulation into D32, which the caller zero-initialises).
 struct RopeArgs { const void* cos; const void* sin; const int64_t* pos; int hd; int cols; };
+struct ResidArgs { const void* R; int64_t ld_r; };
 
 static int gemm_dense(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,
                       int64_t M, int64_t N, int64_t K, const void* bias, int epilogue, float* d_f32_accum,
-                      const int32_t* m_rows_dev, const int32_t* k_rows_dev, void* stream, const RopeArgs* rope) {
+                      const int32_t* m_rows_dev, const int32_t* k_rows_dev, void* stream, const RopeArgs* rope, const ResidArgs* resid = nullptr) {
   LMOD_CHECK_ARG(A && B && (D || d_f32_accum) && M > 0 && N > 0 && K > 0, "lmod_gemm_bf16: null pointer or empty problem");
   LMOD_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0 && N % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) &&
                  (!D || (uintptr_t)D % 16 == 0), "lmod_gemm_bf16: strides / N must be multiples of 8 elements and pointers 16-byte aligned (TMA)");
@@ -713,6 +732,7 @@ static int gemm_dense(const void* A, int64_t lda, int a_mn_major, const void* B,
     p2.M = (int)M; p2.N = (int)N; p2.K = (int)K; p2.beta = epilogue & 1; p2.splits = 1; p2.groups = 1; p2.bn = bn2;
     p2.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
     p2.m_dev = m_rows_dev; p2.k_dev = k_rows_dev;
+    if (resid) { p2.R = (const __nv_bfloat16*)resid->R; p2.ld_r = resid->ld_r; }
     if (rope) { p2.rope_cos = (const __nv_bfloat16*)rope->cos; p2.rope_sin = (const __nv_bfloat16*)rope->sin; p2.rope_pos = rope->pos; p2.rope_hd = rope->hd; p2.rope_cols = rope->cols; }
     return dispatch2(a_mn_major != 0, b_mn_major != 0, ta, tb, p2, (cudaStream_t)stream);
   }
@@ -729,6 +749,7 @@ static int gemm_dense(const void* A, int64_t lda, int a_mn_major, const void* B,
   p.dbg_nostore = getenv("LMOD_GEMM_NOSTORE") ? 1 : 0;
   p.splits = (epilogue >> 8) > 1 ? (epilogue >> 8) : 1;
   p.m_dev = m_rows_dev; p.k_dev = k_rows_dev;
+  if (resid) { p.R = (const __nv_bfloat16*)resid->R; p.ld_r = resid->ld_r; }
   if (rope) { p.rope_cos = (const __nv_bfloat16*)rope->cos; p.rope_sin = (const __nv_bfloat16*)rope->sin; p.rope_pos = rope->pos; p.rope_hd = rope->hd; p.rope_cols = rope->cols; }
   LMOD_CHECK_ARG(p.splits == 1 || d_f32_accum, "lmod_gemm_bf16: split-K needs the fp32 accumulate output");
   const int tiles = (int)(((M + BM - 1) / BM) * ((N + BN - 1) / BN)) * p.splits;
@@ -751,6 +772,16 @@ extern "C" int lmod_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int
   LMOD_CHECK_ARG(hd == 64 || hd == 128, "lmod_gemm_qkv_rope: head_dim %d not fused (64 and 128 are; use lmod_gemm_bf16 + lmod_rope)", hd);
   RopeArgs r = {cos_table, sin_table, position_ids, hd, (nh + nkv) * hd};
   return gemm_dense(A, lda, 0, W, ldb, 0, D, ldd, M, (int64_t)(nh + 2 * nkv) * hd, K, bias, 0, nullptr, nullptr, nullptr, stream, &r);
+}
+
+// D[M,N] = bf16( bf16(A W^T + bias) + R ): a projection whose output goes straight into the residual stream (o_proj / down_proj of
+// Qwen2DecoderLayer, modeling_qwen2.py:796,808; out_proj / fc2 of the CLIP encoder layers).  Bit-identical to lmod_gemm_bf16 followed by
+// lmod_add.  D may alias R (in-place update of the stream: every element is read and written by the same thread).
+extern "C" int lmod_gemm_residual(const void* A, int64_t lda, const void* W, int64_t ldb, const void* bias, const void* R, int64_t ld_r,
+                                  void* D, int64_t ldd, int64_t M, int64_t N, int64_t K, void* stream) {
+  LMOD_CHECK_ARG(R && D && ld_r % 8 == 0 && ((uintptr_t)R % 16 == 0), "lmod_gemm_residual: residual pointer / stride (16-byte rows)");
+  ResidArgs r = {R, ld_r};
+  return gemm_dense(A, lda, 0, W, ldb, 0, D, ldd, M, N, K, bias, 0, nullptr, nullptr, nullptr, stream, nullptr, &r);
 }
 
 extern "C" int lmod_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd,

@@ -42,6 +42,7 @@ struct KlParams {
   // the row count comes from device memory.  null = dense layout, n_rows rows.
   const int32_t* perm;
   const int32_t* count;
+  int keep_tail;         // stream kernel: 1 = the last ring-full of pass-1 chunks stays in shared memory for pass 2 (0: A/B arm, LMOD_KL_KEEP=0)
 };
 
 struct Xchg {            // per-CTA partials published to the cluster
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlP
   len = len < 0 ? 0 : (len > p.slice ? p.slice : len);
   const int nchunks = (len + KS_CH - 1) / KS_CH;
   const bool want_grad = p.d != nullptr;
+  const int held = (want_grad && p.keep_tail) ? min(KS_STAGES, nchunks) : 0;     // pass-1 chunks kept in the ring for pass 2
 
   if (tid == 0) {
     for (int i = 0; i < KS_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], KS_THREADS / 32); }
@@ -517,16 +519,27 @@ __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlP
         if (!kl_row_masks(p, row, orow, lab_next, m_kd, m_ce)) continue;
         const __nv_bfloat16* srow = p.s + row * p.ld_s + v0;
         const __nv_bfloat16* trow = p.t + row * p.ld_t + v0;
-        for (int pass = 0; pass < (want_grad ? 2 : 1); ++pass) {
-          const uint64_t pol = (pass == 0 && want_grad) ? keep : drop;
-          for (int c = 0; c < nchunks; ++c, ++n) {
+        // pass 1: every chunk.  pass 2: the last `held` chunks of pass 1 are still in the ring (their stages are released only after the
+        // gradient pass has used them), so only chunks [0, nchunks - held) are fetched again, into the stages as they come free
+        for (int c = 0; c < nchunks; ++c, ++n) {
+          const uint32_t st = n % KS_STAGES;
+          if (n >= KS_STAGES) ks_wait(&empty[st], ((n / KS_STAGES) - 1) & 1);
+          const int e0 = c * KS_CH, cnt = min(KS_CH, len - e0);
+          uint8_t* sb = smem_raw + (size_t)st * (KS_CH * 4);
+          const uint64_t pol = (want_grad && c < nchunks - held) ? keep : drop;      // what pass 2 re-reads should stay in L2, the rest not
+          mbar_expect_tx(&full[st], (uint32_t)cnt * 4u);
+          bulk_g2s_hint(sb, srow + e0, (uint32_t)cnt * 2u, &full[st], pol);
+          bulk_g2s_hint(sb + KS_CH * 2, trow + e0, (uint32_t)cnt * 2u, &full[st], pol);
+        }
+        if (want_grad) {
+          for (int c = 0; c < nchunks - held; ++c, ++n) {
             const uint32_t st = n % KS_STAGES;
             if (n >= KS_STAGES) ks_wait(&empty[st], ((n / KS_STAGES) - 1) & 1);
             const int e0 = c * KS_CH, cnt = min(KS_CH, len - e0);
             uint8_t* sb = smem_raw + (size_t)st * (KS_CH * 4);
             mbar_expect_tx(&full[st], (uint32_t)cnt * 4u);
-            bulk_g2s_hint(sb, srow + e0, (uint32_t)cnt * 2u, &full[st], pol);
-            bulk_g2s_hint(sb + KS_CH * 2, trow + e0, (uint32_t)cnt * 2u, &full[st], pol);
+            bulk_g2s_hint(sb, srow + e0, (uint32_t)cnt * 2u, &full[st], drop);
+            bulk_g2s_hint(sb + KS_CH * 2, trow + e0, (uint32_t)cnt * 2u, &full[st], drop);
           }
         }
       }
@@ -596,7 +609,7 @@ __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlP
           if (rel < 8u) slab = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s_buf + i)[rel]);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+        if (lane == 0 && c < nchunks - held) mbar_arrive(&empty[st]);       // the held tail is released by pass 2
       }
       float zs = A.zs0 + A.zs1, zt = A.zt0 + A.zt1, acc = A.a0 + A.a1;
       zk += zt;
@@ -666,13 +679,18 @@ __global__ void __launch_bounds__(KS_THREADS + 32, 1) kl_stream_kernel(const KlP
         const float cce = m_ce ? (p.w_ce / n_ce) : 0.f;
         const float ca = ckd + cce, cb = ckd;
         const float es = -lse_s * LOG2E_F, et = -lse_t * LOG2E_F;
-        for (int c = 0; c < nchunks; ++c, ++n) {
-          const uint32_t st = n % KS_STAGES;
+        // first the chunks pass 1 left in the ring (no load, no wait: their stage is the one pass 1 filled), then the rest of the row as the
+        // producer re-fetches it (L2) into the stages released here
+        const uint32_t n_p1 = n - (uint32_t)nchunks;                      // sequence number of this row's first pass-1 chunk
+        for (int q = 0; q < nchunks; ++q) {
+          const bool in_ring = q < held;
+          const int c = in_ring ? nchunks - held + q : q - held;
+          const uint32_t st = (in_ring ? n_p1 + (uint32_t)c : n) % KS_STAGES;
           const int e0 = c * KS_CH, nv = min(KS_CH, len - e0) >> 3;
           const uint4* s_buf = reinterpret_cast<const uint4*>(smem_raw + (size_t)st * (KS_CH * 4));
           const uint4* t_buf = reinterpret_cast<const uint4*>(smem_raw + (size_t)st * (KS_CH * 4) + KS_CH * 2);
           uint4* dst = reinterpret_cast<uint4*>(p.d + row * p.ld_d + v0 + e0);
-          ks_wait(&full[st], (n / KS_STAGES) & 1);
+          if (!in_ring) { ks_wait(&full[st], (n / KS_STAGES) & 1); ++n; }
           for (int i = tid; i < nv; i += KS_THREADS) {
             const uint4 sv = s_buf[i], tv = t_buf[i];
             float g[8];
@@ -841,6 +859,8 @@ extern "C" int lmod_kl_fwd_bwd_rows(const void* s_logits, int64_t ld_s, const vo
   p.s = (const __nv_bfloat16*)s_logits; p.t = (const __nv_bfloat16*)t_logits; p.labels = labels;
   p.counts = counts2; p.row_out = row_out; p.d = (__nv_bfloat16*)dlogits;
   p.ld_s = ld_s; p.ld_t = ld_t; p.ld_d = ld_d; p.n_rows = n_rows; p.seq_len = seq_len;
+  static const int keep_env = getenv("LMOD_KL_KEEP") ? atoi(getenv("LMOD_KL_KEEP")) : 1;
+  p.keep_tail = keep_env;
   p.vocab = (int)vocab; p.slice = slice; p.distill_all = distill_all; p.w_kd = w_kd; p.w_ce = w_ce;
   LMOD_CHECK_ARG((perm == nullptr) == (count == nullptr), "lmod_kl_fwd_bwd_rows: perm and count go together");
   p.perm = perm; p.count = count;

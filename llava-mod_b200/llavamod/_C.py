@@ -61,6 +61,7 @@ SIGNATURES = {
     "lmod_gemm_silu_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _L, _L, _P],
     "lmod_grouped_gemm_silu_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _L, _L, _L, _P],
     "lmod_grouped_gemm_bf16": [_P, _L, _P, _L, _P, _L, _P, _I, _L, _L, _L, _L, _I, _I, _P],
+    "lmod_gemm_residual": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _L, _L, _L, _P],
     "lmod_attn_fwd": [_P, _L, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P, _P],
     "lmod_attn_fwd_trace": [_P, _L, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P],
     "lmod_attn_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P, _P, _P],
@@ -108,7 +109,10 @@ def ptr(t):
 def call(name, *args):
     """Invoke an entry point; append the current stream; raise on a non-zero status."""
     L = lib()
-    rc = getattr(L, name)(*args, stream_ptr())
+    fn = getattr(L, name)
+    if len(args) + 1 != len(fn.argtypes):      # an argument ctypes has no type for would be passed as a 32-bit int (a truncated pointer)
+        raise LmodError("%s takes %d arguments + stream, got %d" % (name, len(fn.argtypes) - 1, len(args)))
+    rc = fn(*args, stream_ptr())
     if rc != 0:
         raise LmodError("%s failed (%d): %s" % (name, rc, L.lmod_last_error().decode()))
 

@@ -139,6 +139,10 @@ def gemm(a, b, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, ou
 # reduction length), "1" always, "0" never; LLAVAMOD_FUSE_ROPE: "0" = GEMM + lmod_rope.
 FUSE_SWIGLU = _os.environ.get("LLAVAMOD_FUSE_SWIGLU", "auto")
 FUSE_ROPE = _os.environ.get("LLAVAMOD_FUSE_ROPE", "auto")
+# residual add in the o_proj / down_proj (CLIP: out_proj / fc2) epilogue of no-grad forwards.  Bit-identical to the add inside the next norm's
+# kernel; measured (profiles/microbench_r2.txt, profiles/ab_bench_r2.txt): the teacher GEMMs run at 0.96 of the tensor peak and have no epilogue
+# slack, so projection + norm is 0.071 vs 0.067 ms with the add in the epilogue and the step does not move (25.0 vs 25.0 samples/s) -> opt-in
+FUSE_RESIDUAL = _os.environ.get("LLAVAMOD_FUSE_RESIDUAL", "0")
 FUSE_MIN_K = 2048
 
 
@@ -226,17 +230,23 @@ class MLPFn(Function):
         return dx, None, None, None, None
 
 
-def mlp(x, w_gu, w_dn, g_gu=None, g_dn=None):
-    """Dense SwiGLU MLP.  Fused SwiGLU epilogues whenever the intermediate size allows; frozen / no-grad calls keep nothing."""
+def mlp(x, w_gu, w_dn, g_gu=None, g_dn=None, res=None):
+    """Dense SwiGLU MLP.  Fused SwiGLU epilogues whenever the intermediate size allows; frozen / no-grad calls keep nothing.
+    res (no-grad calls only, see residual_fusable): the residual stream, added in the down_proj epilogue -- the return value is the new stream."""
     I = w_gu.shape[0] // 2
     grad = torch.is_grad_enabled() and (x.requires_grad or g_gu is not None or g_dn is not None)
+    assert res is None or not grad
     if swiglu_fusable(I, w_gu.shape[1], training=grad):
         if grad:
             return MLPFn.apply(x, w_gu, w_dn, g_gu, g_dn)
         act, _ = gemm_swiglu(_rows(x), w_gu, False)
+        if res is not None:
+            return gemm_residual(act, w_dn, None, res)
         y = gemm(act, w_dn)
         return y if x.dim() == 2 else y.view(*x.shape[:-1], w_dn.shape[0])
     gu = linear(x, w_gu, None, g_gu, None)
+    if res is not None:
+        return gemm_residual(silu_mul(gu), w_dn, None, res)
     return linear(silu_mul(gu), w_dn, None, g_dn, None)
 
 
@@ -287,6 +297,28 @@ def linear(x, w, bias=None, wgrad=None, bgrad=None):
     if torch.is_grad_enabled() and (x.requires_grad or wgrad is not None):
         return LinearFn.apply(x, w, bias, wgrad, bgrad)
     return mm_nt(x, w, bias)
+
+
+def residual_fusable(x, res, *grads):
+    """The projection's epilogue may add the residual stream itself when nothing of the call is differentiated (frozen teacher, CLIP tower,
+    eval): the trainable students keep the add inside the next norm's kernel, whose backward needs the un-added branch anyway."""
+    if FUSE_RESIDUAL != "1" or res is None:
+        return False
+    if not torch.is_grad_enabled():
+        return True
+    return not (x.requires_grad or res.requires_grad or any(g is not None for g in grads))
+
+
+def gemm_residual(x, w, bias, res, inplace=False):
+    """bf16( bf16(x @ w^T + bias) + res ) in one GEMM (lmod_gemm_residual): the output IS the new residual stream (inplace: written over res)."""
+    _need_cuda(x, w, res)
+    x2, r2 = _rows(x), _rows(res)
+    M, Kd = x2.shape
+    N = w.shape[0]
+    out = r2 if inplace else torch.empty(M, N, dtype=x2.dtype, device=x2.device)
+    call("lmod_gemm_residual", ptr(x2), x2.stride(0), ptr(w), w.stride(0), ptr(bias) if bias is not None else None, ptr(r2), r2.stride(0),
+         ptr(out), out.stride(0), M, N, Kd)
+    return out if res.dim() == 2 else out.view(res.shape)
 
 
 # ---------------------------------------------------------------------------------------------------

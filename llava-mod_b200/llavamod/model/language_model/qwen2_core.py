@@ -290,9 +290,14 @@ class Qwen2Model(nn.Module):
                 x, stream = K.rmsnorm(branch, layer.input_layernorm.weight, cfg.rms_norm_eps, res=stream, wgrad=self.gview(layer.input_layernorm.weight))
             qkv = K.qkv_rope(x, at.qkv_weight, at.qkv_bias, cos, sin, pos, nh, nkv, hd, self.gview(at.qkv_weight), self.gview(at.qkv_bias))
             attn = K.attention(qkv, B, T, nh, nkv, hd, True, None, pad)
-            branch = K.linear(attn, at.o_proj.weight, None, self.gview(at.o_proj.weight), None)
-            x, stream = K.rmsnorm(branch, layer.post_attention_layernorm.weight, cfg.rms_norm_eps, res=stream,
-                                  wgrad=self.gview(layer.post_attention_layernorm.weight))
+            if K.residual_fusable(attn, stream, self.gview(at.o_proj.weight), self.gview(layer.post_attention_layernorm.weight)):
+                # frozen / no-grad forward: o_proj's epilogue writes residual + branch (modeling_qwen2.py:796), the norm reads one tensor
+                stream = K.gemm_residual(attn, at.o_proj.weight, None, stream)
+                x, stream = K.rmsnorm(stream, layer.post_attention_layernorm.weight, cfg.rms_norm_eps)
+            else:
+                branch = K.linear(attn, at.o_proj.weight, None, self.gview(at.o_proj.weight), None)
+                x, stream = K.rmsnorm(branch, layer.post_attention_layernorm.weight, cfg.rms_norm_eps, res=stream,
+                                      wgrad=self.gview(layer.post_attention_layernorm.weight))
             mlp = layer.mlp
             if isinstance(mlp, MoE):
                 ds = mlp.deepspeed_moe
@@ -310,6 +315,9 @@ class Qwen2Model(nn.Module):
                                                               cf, mlp.min_capacity)
                     records.append(rec)
                 l_auxes.append(l_aux)
+                branch = None
+            elif K.residual_fusable(x, stream, self.gview(mlp.gu_weight), self.gview(mlp.down_proj.weight)):
+                stream = K.mlp(x, mlp.gu_weight, mlp.down_proj.weight, res=stream)      # down_proj epilogue adds the stream (:808)
                 branch = None
             else:
                 branch = K.mlp(x, mlp.gu_weight, mlp.down_proj.weight, self.gview(mlp.gu_weight), self.gview(mlp.down_proj.weight))

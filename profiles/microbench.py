@@ -100,6 +100,14 @@ def main():
         K.FUSE_ROPE = "0"
         timed("  unfused: gemm + rope", lambda: K.qkv_rope(x, w, b, cos, sin, pos, nh, nh, hd), 2.0 * M * 3 * nh * hd * H, "TFLOP/s")
         K.FUSE_ROPE = "auto"
+    # residual add in the projection's epilogue + plain RMSNorm  vs  projection + RMSNorm that adds the residual (teacher o_proj / down_proj)
+    for (M, N, Kd, tag) in [(T, 4096, 4096, "teacher o_proj"), (T, 4096, 11008, "teacher down_proj"), (577, 1024, 4096, "CLIP fc2")]:
+        x = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
+        w = (torch.randn(N, Kd, device=dev) * 0.02).to(torch.bfloat16)
+        res = torch.randn(M, N, device=dev).to(torch.bfloat16)
+        nw = torch.ones(N, device=dev, dtype=torch.bfloat16)
+        timed("%s %dx%dx%d residual epilogue + rmsnorm" % (tag, M, N, Kd), lambda: K.rmsnorm(K.gemm_residual(x, w, None, res), nw, 1e-6), 2.0 * M * N * Kd, "TFLOP/s")
+        timed("  unfused: gemm + rmsnorm(+residual)", lambda: K.rmsnorm(K.gemm(x, w), nw, 1e-6, res=res), 2.0 * M * N * Kd, "TFLOP/s")
     wgu_e = (torch.randn(4, 5632, 1024, device=dev) * 0.02).to(torch.bfloat16)
     timed("grouped gemm_swiglu 4x[~1024,5632,1024]", lambda: K.grouped_gemm_swiglu(xp, wgu_e, offs, 4608, True), 2.0 * 4096 * 5632 * 1024, "TFLOP/s")
     timed("  unfused: grouped gemm + silu_mul", lambda: K.silu_mul(K.grouped_gemm(xp, wgu_e, h1, offs, 0)), 2.0 * 4096 * 5632 * 1024, "TFLOP/s")

@@ -33,6 +33,23 @@ def test_ctypes_table_matches_header():
     assert _C.lib().lmod_last_error() is not None
 
 
+def test_ctypes_signatures_have_the_arity_of_the_header_prototypes():
+    """An argument ctypes has no declared type for is passed as a 32-bit int -- a truncated pointer (e.g. the stream) that crashes on the GPU
+    box only.  Every ctypes signature must list exactly as many parameters as the prototype in include/lmod.h."""
+    from llavamod import _C
+    src = open(os.path.join(ROOT, "include", "lmod.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    seen = 0
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*|void)\s+(lmod_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        if name not in _C.SIGNATURES:
+            continue
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_C.SIGNATURES[name]) == n, (name, len(_C.SIGNATURES[name]), n)
+        seen += 1
+    assert seen >= 40
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from llavamod import _C
     monkeypatch.setattr(_C, "_lib", None)

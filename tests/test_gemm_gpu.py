@@ -111,6 +111,28 @@ def test_qkv_projection_with_fused_rope(M, H, nh, nkv, hd):
     Kk.FUSE_ROPE = "auto"
 
 
+@pytest.mark.parametrize("M,N,K,bias", [(2048, 4096, 4096, False), (2048, 4096, 11008, False), (2048, 1024, 1024, True), (577, 1024, 4096, True),
+                                        (300, 520, 200, True), (1154, 1024, 1024, True)])
+def test_gemm_with_residual_epilogue_is_gemm_plus_add(M, N, K, bias):
+    """o_proj / down_proj (modeling_qwen2.py:796,808) and CLIP out_proj / fc2 with the residual add in the GEMM epilogue: bit-identical to
+    GEMM (+bias, rounded to bf16) followed by the bf16 add kernel -- CTA-pair tiles (teacher shapes), 1-CTA tiles, ragged edges, in place."""
+    from llavamod import kernels as Kk
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g).to(torch.bfloat16) if bias else None
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    y = Kk.gemm(x, w, bias=b)
+    want = torch.empty_like(res)
+    Kk.call("lmod_add", Kk.ptr(res), Kk.ptr(y), res.numel(), Kk.ptr(want))
+    assert torch.equal(want, (res.float() + y.float()).to(torch.bfloat16))          # the add kernel is the reference's bf16 add
+    got = Kk.gemm_residual(x, w, b, res)
+    assert torch.equal(got, want)
+    r2 = res.clone()
+    out = Kk.gemm_residual(x, w, b, r2, inplace=True)
+    assert out.data_ptr() == r2.data_ptr() and torch.equal(r2, want)
+
+
 def test_grouped_swiglu_forward_and_backward():
     """Expert form on ragged 128-aligned row groups (one empty group): fused == grouped GEMM + element-wise kernels, bit for bit."""
     from llavamod import kernels as Kk

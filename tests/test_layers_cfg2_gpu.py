@@ -62,6 +62,17 @@ def test_teacher_layer_forward_at_7b_shape():
         # rmsnorm, qkv GEMM with the RoPE epilogue, attention, o_proj, rmsnorm(+residual), gate|up GEMM with the SwiGLU epilogue, down GEMM,
         # final norm: the fused-epilogue paths are the ones that ran (separate rope / silu_mul launches would make it 10)
         assert _C.launch_count() - n0 == 8, _C.launch_count() - n0
+        # opt-in variant: the residual adds in the o_proj / down_proj epilogues (modeling_qwen2.py:796,808) -- same launches, same bits as the
+        # add inside the norm kernel
+        from llavamod import kernels as Kk
+        Kk.FUSE_RESIDUAL = "1"
+        try:
+            n0 = _C.launch_count()
+            out_fused, _, _ = m(x.cuda())
+            assert _C.launch_count() - n0 == 8
+        finally:
+            Kk.FUSE_RESIDUAL = "0"
+        assert torch.equal(out, out_fused)
         ref, _ = R.lm_forward(sd, lc, x.float(), None, None)
     assert rel(out, ref) < 1.2e-2, rel(out, ref)
     err = (out.float().cpu() - ref).abs()

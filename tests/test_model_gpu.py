@@ -40,6 +40,16 @@ def test_dense_model_matches_reference_golden(name, golden_dir):
     err = (out.logits.float().cpu() - fx["logits"])[valid].abs().max().item()
     assert err < 3e-2 * fx["logits"][valid].abs().max().item() + 3e-2, err
     assert abs(out.loss.item() - fx["loss"].item()) < 1e-2 * fx["loss"].item()
+    # opt-in: residual adds in the projection epilogues (CLIP out_proj / fc2, decoder o_proj / down_proj) -- the same bits end to end
+    from llavamod import kernels as Kk
+    Kk.FUSE_RESIDUAL = "1"
+    try:
+        with torch.no_grad():
+            out2 = m(input_ids=fx["input_ids"], labels=fx["labels"], attention_mask=fx["attention_mask"],
+                     images=[im.to(torch.bfloat16) for im in fx["images"]], return_dict=True)
+    finally:
+        Kk.FUSE_RESIDUAL = "0"
+    assert torch.equal(out.logits, out2.logits)
 
 
 def test_student_forward_and_trainer_loss_match_oracle():
