@@ -97,7 +97,7 @@ int lmod_align_loss_dense(const float* logp, const float* probs, int64_t ld, con
                           float* out_loss, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * K10 + K11: DeepSpeed-0.9.5 top-2 gate + capacity + token scatter in ONE cooperative kernel.
+ * K10 + K11: DeepSpeed-0.9.5 top-2 gate + capacity + token scatter in one call (two plain launches: gate, then seat+scatter).
  * Replaces deepspeed.moe.sharded_moe.TopKGate/top2gating + the dispatch einsum
  * (call site llava_qwen1_5_moe.py:536-546).
  *   x [S,H] bf16, wg [E,H] fp32, noise [S,E] fp32 (Gumbel, explicit input).

@@ -865,7 +865,7 @@ extern "C" int lmod_kl_fwd_bwd_rows(const void* s_logits, int64_t ld_s, const vo
   LMOD_CHECK_ARG((perm == nullptr) == (count == nullptr), "lmod_kl_fwd_bwd_rows: perm and count go together");
   p.perm = perm; p.count = count;
 
-  // LMOD_KL_MODE: unset / "stream" = the streaming kernel (2 CTAs per row, ring + L2 re-read); "stream1" / "stream4" = 1 / 4 CTAs per row;
+  // LMOD_KL_MODE: unset / "stream" = the streaming kernel (1 CTA per row, ring + L2 re-read); "stream2" / "stream4" = 2 / 4 CTAs per row;
   // "sb128" the round-1 shared-memory-resident 8-CTA kernel (kept as the A/B arm of profiles/kl_bench.py), "sb256"/"sb384"/"sb512" its
   // thread-count variants, "db256"/"db512" its double-buffered experiments
   static const char* mode_env = getenv("LMOD_KL_MODE");
