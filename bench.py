@@ -273,7 +273,10 @@ def our_config(wl_name, accum, world, cuda_graphs=True, compact=True):
     return {"workload": wl_name, "student": wl["student"] + "-%dE-top2" % wl["experts"], "teacher": wl["teacher"], "vision": wl["clip"],
             "seq_len": wl["seq"], "micro_batch": 1, "grad_accum": accum, "global_batch": accum * world,
             "loss": {"mimic": "kd_lm (mimic KL + LM + aux)", "dpo": "sigmoid DPO + aux", "mimic+dpo": "kd_lm micro-batches + sigmoid-DPO pairs"}[wl["kind"]],
-            "parallelism": "dp%d" % world}
+            "parallelism": "dp%d" % world,
+            # timing rule: no explicit L2 flush between timed steps -- one step streams the 15.4 GB of frozen teacher weights, the student's
+            # weights / gradients / optimizer arenas and ~2 GB of activations and logits per micro-batch through a 126 MB L2
+            "l2": "inputs larger than L2 (>= 17 GB touched per micro-batch); no flush"}
 
 
 def run_reference(args):
