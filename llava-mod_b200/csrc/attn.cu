@@ -279,6 +279,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       l0 = fmaf(l0, alpha, rs0);
       l1 = fmaf(l1, alpha, rs1);
       ATT_TRACE(4);
+      // P_j (bf16x2) over the start of S_j: group g -> columns [16g, 16g+16).  Issued before the (rare) O rescale so that the 16 packed
+      // registers are dead while the rescale holds 32 accumulator columns (the 96-register build of hd 128 spilled across it)
+      tmem_st16(tS0 + s * BKV + g * 16 + lane_off, pk);
       if (j > 0) {
         const bool any_upd = __any_sync(0xffffffffu, upd);
         if (any_upd || j == nblk - 1) {                      // (the last block always waits: it keeps the epilogue's parity wait unambiguous)
@@ -301,7 +304,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
       }
       ATT_TRACE(5);
-      tmem_st16(tS0 + s * BKV + g * 16 + lane_off, pk);      // P_j (bf16x2) over the start of S_j: group g -> columns [16g, 16g+16)
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
